@@ -1,0 +1,174 @@
+"""ctypes binding of libcerberus_costvolume.so (the C ABI in include/cerberus_costvolume.h).
+
+The library is the product: there is no CPU or PyTorch fallback.  If it is missing it is built
+in-tree with nvcc; if that fails, or a tensor is not on a CUDA device, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+
+CERB_F32, CERB_F16, CERB_BF16 = 0, 1, 2
+WARP_TORCH, WARP_TRT = 0, 1
+VARIANT_AUTO, VARIANT_FAST, VARIANT_FAST_NOTMA, VARIANT_SMALL, VARIANT_SMALL_NOTMA, VARIANT_GENERIC = range(6)
+
+_DTYPES = {torch.float32: CERB_F32, torch.float16: CERB_F16, torch.bfloat16: CERB_BF16}
+
+
+class CorrParams(ctypes.Structure):
+    """struct cerb_corr_params (include/cerberus_costvolume.h)."""
+    _fields_ = [
+        ("batch", ctypes.c_int32), ("channels", ctypes.c_int32), ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("pad_size", ctypes.c_int32), ("kernel_size", ctypes.c_int32), ("max_displacement", ctypes.c_int32),
+        ("stride1", ctypes.c_int32), ("stride2", ctypes.c_int32), ("corr_multiply", ctypes.c_int32),
+        ("dtype", ctypes.c_int32), ("warp_mode", ctypes.c_int32), ("leaky_slope", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
+        ("x1_stride", ctypes.c_int64 * 4), ("x2_stride", ctypes.c_int64 * 4),
+        ("flow_stride", ctypes.c_int64 * 4), ("out_stride", ctypes.c_int64 * 4),
+    ]
+
+
+class TrtDims(ctypes.Structure):
+    _fields_ = [("nbDims", ctypes.c_int32), ("d", ctypes.c_int32 * 8)]
+
+
+class TrtTensorDesc(ctypes.Structure):
+    """Layout of nvinfer1::PluginTensorDesc (TensorRT 7/8)."""
+    _fields_ = [("dims", TrtDims), ("type", ctypes.c_int32), ("format", ctypes.c_int32), ("scale", ctypes.c_float)]
+
+
+class TrtCorrFields(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("pad_size", "kernel_size", "max_displacement", "stride1", "stride2", "corr_multiply")]
+
+
+EXPORTS = [
+    "cerb_abi_version", "cerb_error_string", "cerb_corr_output_dims", "cerb_warp_corr_forward",
+    "cerb_warp_corr_forward_variant", "cerb_warp_corr_backward_workspace", "cerb_warp_corr_backward",
+    "cerb_flow_warp_forward", "cerb_flow_warp_backward", "cerb_warp_corr_forward_host_workspace",
+    "cerb_warp_corr_forward_host", "cerb_launch_count",
+    "cerb_trt_corr_default_fields", "cerb_trt_corr_serialization_size", "cerb_trt_corr_serialize",
+    "cerb_trt_corr_deserialize", "cerb_trt_corr_output_dims", "cerb_trt_corr_supports_format",
+    "cerb_trt_corr_workspace_size", "cerb_trt_corr_enqueue", "cerb_trt_corr_enqueue_i64",
+    "cerb_trt_warp_corr_enqueue",
+]
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (building first if needed) the shared library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        path = _build.build_library()
+    L = ctypes.CDLL(path)
+    vp, i32, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p
+    pp = ctypes.POINTER(CorrParams)
+    L.cerb_abi_version.restype = ctypes.c_int
+    L.cerb_error_string.restype = ctypes.c_char_p
+    L.cerb_error_string.argtypes = [ctypes.c_int]
+    L.cerb_corr_output_dims.argtypes = [pp] + [ctypes.POINTER(i32)] * 3
+    L.cerb_warp_corr_forward.argtypes = [pp, vp, vp, f32p, vp, vp]
+    L.cerb_warp_corr_forward_variant.argtypes = [pp, vp, vp, f32p, vp, ctypes.c_int, vp]
+    L.cerb_warp_corr_backward_workspace.argtypes = [pp, ctypes.c_int]
+    L.cerb_warp_corr_backward_workspace.restype = ctypes.c_size_t
+    L.cerb_warp_corr_backward.argtypes = [pp, vp, vp, f32p, vp, vp, vp, vp, f32p, vp, ctypes.c_size_t, vp]
+    L.cerb_flow_warp_forward.argtypes = [vp, f32p, vp, i32, i32, i32, i32, i32, i32, vp]
+    L.cerb_flow_warp_backward.argtypes = [vp, f32p, vp, vp, f32p, i32, i32, i32, i32, i32, i32, vp]
+    L.cerb_warp_corr_forward_host_workspace.argtypes = [pp, ctypes.c_int]
+    L.cerb_warp_corr_forward_host_workspace.restype = ctypes.c_size_t
+    L.cerb_warp_corr_forward_host.argtypes = [pp, vp, vp, f32p, vp, vp, ctypes.c_size_t, vp]
+    L.cerb_launch_count.restype = ctypes.c_uint64
+    fp = ctypes.POINTER(TrtCorrFields)
+    dp = ctypes.POINTER(TrtTensorDesc)
+    L.cerb_trt_corr_default_fields.argtypes = [fp]
+    L.cerb_trt_corr_default_fields.restype = None
+    L.cerb_trt_corr_serialization_size.restype = ctypes.c_size_t
+    L.cerb_trt_corr_serialize.argtypes = [fp, vp]
+    L.cerb_trt_corr_serialize.restype = ctypes.c_size_t
+    L.cerb_trt_corr_deserialize.argtypes = [vp, ctypes.c_size_t, fp]
+    L.cerb_trt_corr_output_dims.argtypes = [fp, ctypes.POINTER(TrtDims), ctypes.POINTER(TrtDims)]
+    L.cerb_trt_corr_supports_format.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_int]
+    L.cerb_trt_corr_workspace_size.argtypes = [fp, dp, ctypes.c_int, dp, ctypes.c_int]
+    L.cerb_trt_corr_workspace_size.restype = ctypes.c_size_t
+    L.cerb_trt_corr_enqueue.argtypes = [fp, dp, dp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+    L.cerb_trt_warp_corr_enqueue.argtypes = [fp, i32, ctypes.c_float, dp, dp, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                             vp, vp]
+    if L.cerb_abi_version() != 1:
+        raise RuntimeError("libcerberus_costvolume.so: ABI version mismatch")
+    _lib = L
+    return L
+
+
+class CostVolumeError(RuntimeError):
+    """Raised when the C ABI returns non-zero (the reference raises RuntimeError through
+    AT_ERROR, correlation_cuda.cpp:22-23)."""
+
+
+def check(code: int, what: str):
+    if code != 0:
+        msg = lib().cerb_error_string(code).decode()
+        raise CostVolumeError(f"{what} failed: {msg} (code {code})")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise CostVolumeError(f"unsupported dtype {t.dtype}: float32, float16 and bfloat16 are implemented") from None
+
+
+def require_cuda(*tensors: torch.Tensor):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise CostVolumeError("cerberusnet_b200 has no CPU path: tensors must live on a CUDA device "
+                                  "(reference op is CUDA-only too, correlation_cuda.cpp:45-48)")
+
+
+def _strides(t: Optional[torch.Tensor]):
+    if t is None:
+        return (ctypes.c_int64 * 4)(0, 0, 0, 0)
+    return (ctypes.c_int64 * 4)(*t.stride())
+
+
+def make_params(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor],
+                pad_size: int, kernel_size: int, max_displacement: int, stride1: int, stride2: int,
+                corr_multiply: int, warp_mode: int, leaky_slope: Optional[float]) -> CorrParams:
+    B, C, H, W = x1.shape
+    p = CorrParams()
+    p.batch, p.channels, p.height, p.width = B, C, H, W
+    p.pad_size, p.kernel_size, p.max_displacement = int(pad_size), int(kernel_size), int(max_displacement)
+    p.stride1, p.stride2, p.corr_multiply = int(stride1), int(stride2), int(corr_multiply)
+    p.dtype = dtype_code(x1)
+    p.warp_mode = int(warp_mode)
+    p.leaky_slope = math.nan if leaky_slope is None else float(leaky_slope)
+    p.reserved = 0
+    p.x1_stride = _strides(x1)
+    p.x2_stride = _strides(x2)
+    p.flow_stride = _strides(flow)
+    p.out_stride = _strides(out)
+    return p
+
+
+def output_dims(p: CorrParams):
+    oc, oh, ow = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    check(lib().cerb_corr_output_dims(ctypes.byref(p), ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)),
+          "cerb_corr_output_dims")
+    return oc.value, oh.value, ow.value
+
+
+def current_stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,174 @@
+// costvolume_common.cuh -- shared device helpers for the sm_100a cost-volume kernels.
+//
+// Semantics restated from SURVEY.md section 8(a); reference sites (relative to the reference
+// checkout) are cited next to the arithmetic they pin.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/cerberus_costvolume.h"
+
+namespace cerb {
+
+// ---------------------------------------------------------------- element I/O -------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T> __device__ __forceinline__ float ldg_f32(const T* p) { return to_f32<T>(__ldg(p)); }
+
+// ---------------------------------------------------------------- problem geometry --------
+struct Geom {
+  int B, C, H, W;            // inputs
+  int pad, k, md, s1, s2;    // correlation parameters
+  int kr, r, D, D2;          // kernel radius, displacement radius (md / s2), 2r+1, D*D
+  int outH, outW;
+  int warp_mode;             // CERB_WARP_*
+  int has_act;               // LeakyReLU fused
+  float slope;
+  float inv_unused;          // keep the struct 8-byte friendly
+  long long x1s[3], x2s[3], fls[3], os[3];  // N, C, H strides in elements (W stride == 1)
+};
+
+// ---------------------------------------------------------------- flow warp ---------------
+// Sample position along one axis for output pixel `pix` displaced by `disp`.
+//   grid  g = 2*(pix+disp)/(size-1) - 1         UnFlowLoss.py:16-19,30-31,89-91 (three separate
+//                                               fp32 roundings: separate torch kernels)
+//   TORCH p = ((g+1)*size - 1)/2                ATen grid_sampler_unnormalize(align_corners=False)
+//                                               (compiled with -fmad: one FMA)
+//   TRT   p = ((g+1)*(size-1))/2                trt_plugins/grid_sampler.cu:55-58
+//   border clip to [0,size-1]                   clip_coordinates; grid_sampler.cu:62-64
+// inside = un-clipped position strictly inside (0,size-1) -> gradient passes (ATen
+// clip_coordinates_set_grad), else zero.
+__device__ __forceinline__ float sample_pos(int pix, float disp, int size, int mode, bool& inside) {
+  float v = __fadd_rn((float)pix, disp);
+  v = __fmul_rn(2.0f, v);
+  v = __fdiv_rn(v, (float)(size - 1));
+  const float g = __fadd_rn(v, -1.0f);
+  float p;
+  if (mode == CERB_WARP_TRT)
+    p = __fdiv_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)(size - 1)), 2.f);
+  else
+    p = __fdiv_rn(__fmaf_rn(__fadd_rn(g, 1.f), (float)size, -1.f), 2.f);
+  const float hi = (float)(size - 1);
+  inside = (p > 0.f) && (p < hi);
+  return fminf(hi, fmaxf(p, 0.f));
+}
+
+__device__ __forceinline__ float pos_scale(int size, int mode) {
+  return (mode == CERB_WARP_TRT) ? 1.0f : __fdiv_rn((float)size, (float)(size - 1));
+}
+
+// Bilinear tap set of one warped position: offsets (within one H*W plane, using the H stride)
+// of the 4 taps and their weights, in ATen order nw, ne, sw, se
+// (weights: nw=(x_se-x)*(y_se-y) ... ; a tap outside the image gets weight 0 and a clamped,
+// always-dereferenceable offset).
+struct Taps {
+  int off[4];
+  float w[4];
+};
+
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int H, int W, long long hstride) {
+  const float fx = floorf(ix), fy = floorf(iy);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const int x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = (float)x1 - ix, wx0 = ix - (float)x0;
+  const float wy1 = (float)y1 - iy, wy0 = iy - (float)y0;
+  const bool bx1 = x1 < W, by1 = y1 < H;  // x0,y0 are in range after the clip
+  const int cx1 = bx1 ? x1 : x0, cy1 = by1 ? y1 : y0;
+  Taps t;
+  t.off[0] = (int)(y0 * hstride) + x0;
+  t.off[1] = (int)(y0 * hstride) + cx1;
+  t.off[2] = (int)(cy1 * hstride) + x0;
+  t.off[3] = (int)(cy1 * hstride) + cx1;
+  t.w[0] = wx1 * wy1;
+  t.w[1] = bx1 ? wx0 * wy1 : 0.f;
+  t.w[2] = by1 ? wx1 * wy0 : 0.f;
+  t.w[3] = (bx1 && by1) ? wx0 * wy0 : 0.f;
+  return t;
+}
+
+// acc = 0; acc += v_nw*w_nw; ... in ATen's order (each step one FMA under -fmad).
+__device__ __forceinline__ float blend(float v0, float v1, float v2, float v3, const Taps& t) {
+  float a = __fmul_rn(v0, t.w[0]);
+  a = __fmaf_rn(v1, t.w[1], a);
+  a = __fmaf_rn(v2, t.w[2], a);
+  a = __fmaf_rn(v3, t.w[3], a);
+  return a;
+}
+
+__device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// ---------------------------------------------------------------- PTX wrappers ------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// TMA: 4-D tiled load global -> shared, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// TMA: 4-D tiled store shared -> global (SASS: UTMASTG); out-of-range elements are clipped
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace cerb

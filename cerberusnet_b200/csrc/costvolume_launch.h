@@ -1,0 +1,36 @@
+// costvolume_launch.h -- internal seam between the C ABI (costvolume_api.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "costvolume_common.cuh"
+
+// Forward kernel variants; AUTO is what the product uses, the others exist so tests and the
+// bench can pin a path (cerb_warp_corr_forward_variant).
+enum {
+  CERB_FWD_VARIANT_AUTO = 0,
+  CERB_FWD_VARIANT_FAST = 1,        // 8x32 tiles, TMA in/out when alignment allows
+  CERB_FWD_VARIANT_FAST_NOTMA = 2,  // 8x32 tiles, LDG/STG staging
+  CERB_FWD_VARIANT_SMALL = 3,       // 4x16 tiles, channels split 4-way inside the CTA
+  CERB_FWD_VARIANT_SMALL_NOTMA = 4,
+  CERB_FWD_VARIANT_GENERIC = 5      // one thread per output element, any parameters
+};
+
+namespace cerb {
+
+cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
+                                     void* out, int variant, cudaStream_t stream);
+
+// workspace: fp32 [B,C,H,W] accumulation buffer for grad_x2 when dtype is 16-bit and flow != NULL
+cudaError_t launch_warp_corr_backward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
+                                      const void* out, const void* gout, void* gx1, void* gx2, float* gflow,
+                                      void* workspace, cudaStream_t stream);
+
+cudaError_t launch_flow_warp_forward(int dtype, const void* image, const float* flow, void* out, int B, int C, int H,
+                                     int W, int mode, cudaStream_t stream);
+cudaError_t launch_flow_warp_backward(int dtype, const void* image, const float* flow, const void* gout, void* gimage,
+                                      float* gflow, int B, int C, int H, int W, int mode, cudaStream_t stream);
+
+void count_launches(int n);
+
+}  // namespace cerb

@@ -1,0 +1,130 @@
+"""Functional layer over the C ABI: tensors in, tensors out, current CUDA stream.
+
+These are thin: argument normalisation, output allocation, one C call.  No math happens in
+Python and nothing here falls back to PyTorch ops.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TRT, CostVolumeError, check, current_stream_ptr, lib, make_params,
+                   output_dims, ptr, require_cuda)
+
+__all__ = ["warp_corr_forward", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
+           "WARP_TORCH", "WARP_TRT"]
+
+
+def _inner_contig(t: torch.Tensor) -> torch.Tensor:
+    """The ABI needs W-stride 1 (N/C/H strides are free)."""
+    if t.dim() != 4:
+        raise CostVolumeError(f"expected a 4-D NCHW tensor, got shape {tuple(t.shape)}")
+    return t if (t.stride(3) == 1 and min(t.stride()) >= 0) else t.contiguous()
+
+
+def corr_output_shape(x_shape, pad_size, kernel_size, max_displacement, stride1, stride2) -> Tuple[int, int, int, int]:
+    """(B, D*D, outH, outW) by the reference rule (correlation_cuda.cpp:6-14)."""
+    B, C, H, W = x_shape
+    p = _lib.CorrParams()
+    p.batch, p.channels, p.height, p.width = B, C, H, W
+    p.pad_size, p.kernel_size, p.max_displacement, p.stride1, p.stride2 = (
+        int(pad_size), int(kernel_size), int(max_displacement), int(stride1), int(stride2))
+    oc, oh, ow = output_dims(p)
+    return B, oc, oh, ow
+
+
+def warp_corr_forward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor] = None, pad_size: int = 4,
+                      kernel_size: int = 1, max_displacement: int = 4, stride1: int = 1, stride2: int = 1,
+                      corr_multiply: int = 1, warp_mode: int = WARP_TORCH, leaky_slope: Optional[float] = None,
+                      out: Optional[torch.Tensor] = None, variant: int = VARIANT_AUTO) -> torch.Tensor:
+    """leaky_relu(correlation(x1, flow_warp(x2, flow))) in one kernel launch.
+
+    ``flow=None`` skips the warp, ``leaky_slope=None`` skips the activation; with both off this is
+    the reference's ``torch.ops.cerberus.correlation`` (correlation_cuda.cpp:3-26).
+    ``out`` may be a channel slice of a wider buffer (e.g. the decoder's concat tensor).
+    """
+    require_cuda(x1, x2, flow, out)
+    if x1.shape != x2.shape:
+        raise CostVolumeError(f"input shapes differ: {tuple(x1.shape)} vs {tuple(x2.shape)}")
+    if x1.dtype != x2.dtype:
+        raise CostVolumeError(f"input dtypes differ: {x1.dtype} vs {x2.dtype}")
+    x1, x2 = _inner_contig(x1), _inner_contig(x2)
+    if flow is not None:
+        if flow.shape != (x1.shape[0], 2, x1.shape[2], x1.shape[3]):
+            raise CostVolumeError(f"flow must be (B,2,H,W), got {tuple(flow.shape)}")
+        flow = _inner_contig(flow.float())
+    shape = corr_output_shape(x1.shape, pad_size, kernel_size, max_displacement, stride1, stride2)
+    if out is None:
+        out = torch.empty(shape, dtype=x1.dtype, device=x1.device)
+    elif tuple(out.shape) != shape or out.dtype != x1.dtype or out.stride(3) != 1:
+        raise CostVolumeError(f"out must be {shape} {x1.dtype} with unit W stride")
+    p = make_params(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
+                    warp_mode, leaky_slope)
+    with torch.cuda.device(x1.device):
+        rc = lib().cerb_warp_corr_forward_variant(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow), ptr(out), int(variant),
+                                                  ctypes.c_void_p(current_stream_ptr(x1.device)))
+    check(rc, "cerb_warp_corr_forward")
+    return out
+
+
+def warp_corr_backward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor],
+                       grad_out: torch.Tensor, pad_size: int = 4, kernel_size: int = 1, max_displacement: int = 4,
+                       stride1: int = 1, stride2: int = 1, corr_multiply: int = 1, warp_mode: int = WARP_TORCH,
+                       leaky_slope: Optional[float] = None):
+    """Gradients of :func:`warp_corr_forward`: ``(grad_x1, grad_x2, grad_flow or None)``."""
+    require_cuda(x1, x2, flow, out, grad_out)
+    x1, x2 = _inner_contig(x1), _inner_contig(x2)
+    if flow is not None:
+        flow = _inner_contig(flow.float())
+    grad_out = grad_out.contiguous()
+    if out is not None:
+        out = out.contiguous()
+    if leaky_slope is not None and out is None:
+        raise CostVolumeError("the activated forward output is needed for the LeakyReLU backward")
+    p = make_params(x1, x2, flow, grad_out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
+                    warp_mode, leaky_slope)
+    g1 = torch.empty(x1.shape, dtype=x1.dtype, device=x1.device)
+    g2 = torch.empty(x2.shape, dtype=x2.dtype, device=x2.device)
+    gflow = torch.empty(flow.shape, dtype=torch.float32, device=x1.device) if flow is not None else None
+    need = lib().cerb_warp_corr_backward_workspace(ctypes.byref(p), 1 if flow is not None else 0)
+    ws = torch.empty(need, dtype=torch.uint8, device=x1.device) if need else None
+    with torch.cuda.device(x1.device):
+        rc = lib().cerb_warp_corr_backward(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow), ptr(out), ptr(grad_out),
+                                           ptr(g1), ptr(g2), ptr(gflow), ptr(ws), need,
+                                           ctypes.c_void_p(current_stream_ptr(x1.device)))
+    check(rc, "cerb_warp_corr_backward")
+    return g1, g2, gflow
+
+
+def flow_warp_forward(image: torch.Tensor, flow: torch.Tensor, warp_mode: int = WARP_TORCH) -> torch.Tensor:
+    require_cuda(image, flow)
+    image = image.contiguous()
+    flow = flow.float().contiguous()
+    B, C, H, W = image.shape
+    if flow.shape != (B, 2, H, W):
+        raise CostVolumeError(f"flow must be (B,2,H,W), got {tuple(flow.shape)}")
+    out = torch.empty_like(image)
+    with torch.cuda.device(image.device):
+        rc = lib().cerb_flow_warp_forward(ptr(image), ptr(flow), ptr(out), B, C, H, W, _lib.dtype_code(image),
+                                          int(warp_mode), ctypes.c_void_p(current_stream_ptr(image.device)))
+    check(rc, "cerb_flow_warp_forward")
+    return out
+
+
+def flow_warp_backward(image: torch.Tensor, flow: torch.Tensor, grad_out: torch.Tensor, warp_mode: int = WARP_TORCH):
+    require_cuda(image, flow, grad_out)
+    image = image.contiguous()
+    flow = flow.float().contiguous()
+    grad_out = grad_out.contiguous()
+    B, C, H, W = image.shape
+    gimg = torch.empty_like(image)
+    gflow = torch.empty_like(flow)
+    with torch.cuda.device(image.device):
+        rc = lib().cerb_flow_warp_backward(ptr(image), ptr(flow), ptr(grad_out), ptr(gimg), ptr(gflow), B, C, H, W,
+                                           _lib.dtype_code(image), int(warp_mode),
+                                           ctypes.c_void_p(current_stream_ptr(image.device)))
+    check(rc, "cerb_flow_warp_backward")
+    return gimg, gflow
