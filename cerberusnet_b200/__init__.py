@@ -5,7 +5,7 @@ the LeakyReLU(0.1) that follows it, behind the reference's own Python surfaces
 (``Correlation`` / ``CorrelationFunction`` / ``flow_warp``) and a C ABI
 (``include/cerberus_costvolume.h``) shaped for the TensorRT correlation plugin's ``enqueue``.
 """
-from ._lib import WARP_TORCH, WARP_TRT, CostVolumeError, lib  # noqa: F401
+from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, lib  # noqa: F401
 from .correlation import (Correlation, CorrelationFunction, CorrelationTorch, WarpCorrelation,  # noqa: F401
                           WarpCorrelationFunction, warp_correlation)
 from .flow_warp import FlowWarpFunction, flow_warp, mesh_grid, norm_grid  # noqa: F401

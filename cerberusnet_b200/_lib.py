@@ -15,7 +15,7 @@ import torch
 from . import build as _build
 
 CERB_F32, CERB_F16, CERB_BF16 = 0, 1, 2
-WARP_TORCH, WARP_TRT = 0, 1
+WARP_TORCH, WARP_TRT, WARP_TORCH_CPU = 0, 1, 2
 VARIANT_AUTO, VARIANT_FAST, VARIANT_FAST_NOTMA, VARIANT_SMALL, VARIANT_SMALL_NOTMA, VARIANT_GENERIC = range(6)
 
 _DTYPES = {torch.float32: CERB_F32, torch.float16: CERB_F16, torch.bfloat16: CERB_BF16}

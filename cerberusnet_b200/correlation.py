@@ -13,10 +13,10 @@ from typing import Optional
 import torch
 
 from . import ops
-from ._lib import WARP_TORCH, WARP_TRT
+from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT
 
 __all__ = ["Correlation", "CorrelationFunction", "CorrelationTorch", "WarpCorrelation", "WarpCorrelationFunction",
-           "warp_correlation", "WARP_TORCH", "WARP_TRT"]
+           "warp_correlation", "WARP_TORCH", "WARP_TRT", "WARP_TORCH_CPU"]
 
 
 def _register_ops():

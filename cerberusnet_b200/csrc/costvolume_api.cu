@@ -33,7 +33,7 @@ static int build_geom(const cerb_corr_params* p, bool has_flow, Geom& g) {
   if (p->dtype != CERB_F32 && p->dtype != CERB_F16 && p->dtype != CERB_BF16) return CERB_EINVAL;
   if (p->reserved != 0) return CERB_EINVAL;
   if (has_flow) {
-    if (p->warp_mode != CERB_WARP_TORCH && p->warp_mode != CERB_WARP_TRT) return CERB_EINVAL;
+    if (p->warp_mode < CERB_WARP_TORCH || p->warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
     if (p->height < 2 || p->width < 2) return CERB_EINVAL;  // grid normalisation divides by size-1
   }
   g.B = p->batch; g.C = p->channels; g.H = p->height; g.W = p->width;
@@ -49,7 +49,7 @@ static int build_geom(const cerb_corr_params* p, bool has_flow, Geom& g) {
   g.warp_mode = p->warp_mode;
   g.has_act = (p->leaky_slope == p->leaky_slope) && p->leaky_slope >= 0.f;  // NaN / negative = off
   g.slope = g.has_act ? p->leaky_slope : 1.f;
-  g.inv_unused = 0.f;
+  g.unnorm_fma = 1;
   bool ok1, ok2, ok3, ok4;
   fill_strides(p->x1_stride, g.x1s, g.C, g.H, g.W, ok1);
   fill_strides(p->x2_stride, g.x2s, g.C, g.H, g.W, ok2);
@@ -186,7 +186,7 @@ int cerb_warp_corr_backward(const cerb_corr_params* p, const void* x1, const voi
 int cerb_flow_warp_forward(const void* image, const float* flow, void* out, int32_t batch, int32_t channels,
                            int32_t height, int32_t width, int32_t dtype, int32_t warp_mode, cerb_stream_t stream) {
   if (!image || !flow || !out || batch < 1 || channels < 1 || height < 2 || width < 2) return CERB_EINVAL;
-  if (warp_mode != CERB_WARP_TORCH && warp_mode != CERB_WARP_TRT) return CERB_EINVAL;
+  if (warp_mode < 0 || warp_mode > 7) return CERB_EINVAL;  // bit 2 (4): experiment switch, un-normalise without FMA
   if ((long long)channels * height * width >= 0x7fffffffLL) return CERB_ESTRIDE;
   return (int)launch_flow_warp_forward(dtype, image, flow, out, batch, channels, height, width, warp_mode,
                                        (cudaStream_t)stream);
@@ -197,7 +197,7 @@ int cerb_flow_warp_backward(const void* image, const float* flow, const void* gr
                             int32_t dtype, int32_t warp_mode, cerb_stream_t stream) {
   if (!image || !flow || !grad_out || !grad_image || !grad_flow || batch < 1 || channels < 1 || height < 2 || width < 2)
     return CERB_EINVAL;
-  if (warp_mode != CERB_WARP_TORCH && warp_mode != CERB_WARP_TRT) return CERB_EINVAL;
+  if (warp_mode < CERB_WARP_TORCH || warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
   if ((long long)channels * height * width >= 0x7fffffffLL) return CERB_ESTRIDE;
   return (int)launch_flow_warp_backward(dtype, image, flow, grad_out, grad_image, grad_flow, batch, channels, height,
                                         width, warp_mode, (cudaStream_t)stream);
@@ -248,6 +248,9 @@ int cerb_warp_corr_forward_host(const cerb_corr_params* p, const void* h_x1, con
   if ((e = cudaMemcpyAsync(h_out, d_out, out_raw, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
   return CERB_OK;
 }
+
+// Debugging aid, not part of the public ABI: per-CTA clock64() trace of the fast forward kernel.
+CERB_API void cerb_debug_set_trace_buffer(void* dev_ptr) { cerb::set_trace_buffer((long long*)dev_ptr); }
 
 uint64_t cerb_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 
@@ -318,7 +321,7 @@ int cerb_trt_warp_corr_enqueue(const cerb_trt_corr_fields* f, int32_t warp_mode,
                                const cerb_trt_tensor_desc* input_desc, const cerb_trt_tensor_desc* output_desc,
                                const void* const* inputs, void* const* outputs, void* /*workspace*/,
                                cerb_stream_t stream) {
-  if (warp_mode != CERB_WARP_TORCH && warp_mode != CERB_WARP_TRT) return CERB_EINVAL;
+  if (warp_mode < CERB_WARP_TORCH || warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
   return trt_enqueue_impl(f, warp_mode, leaky_slope, true, input_desc, output_desc, inputs, outputs, stream);
 }
 

@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict_
     const int y = (int)(rem / W), x = (int)(rem - (long long)y * W);
     const float* fp = flow + (long long)n * 2 * plane + rem;
     bool in_x, in_y;
-    const float sx = sample_pos(x, __ldg(fp), W, mode, in_x);
-    const float sy = sample_pos(y, __ldg(fp + plane), H, mode, in_y);
+    const float sx = sample_pos(x, __ldg(fp), W, mode & 3, in_x, !(mode & 4));
+    const float sy = sample_pos(y, __ldg(fp + plane), H, mode & 3, in_y, !(mode & 4));
     const Taps tp = make_taps(sx, sy, H, W, W);
     const T* ip = img + (long long)n * C * plane;
     T* op = out + (long long)n * C * plane + rem;

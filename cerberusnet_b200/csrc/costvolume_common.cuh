@@ -35,31 +35,47 @@ struct Geom {
   int warp_mode;             // CERB_WARP_*
   int has_act;               // LeakyReLU fused
   float slope;
-  float inv_unused;          // keep the struct 8-byte friendly
+  int unnorm_fma;            // ATen un-normalise ((g+1)*size-1)/2 contracted to one FMA (nvcc -fmad) or not
   long long x1s[3], x2s[3], fls[3], os[3];  // N, C, H strides in elements (W stride == 1)
 };
 
 // ---------------------------------------------------------------- flow warp ---------------
+// a / c correctly rounded (Markstein: q = a*rc, r = a - q*c exact by FMA, q' = q + r*rc) for a
+// finite, non-tiny `a`, a positive integer-valued `c` and rc = RN(1/c).  Same bits as IEEE
+// division without its multi-branch slow path; used where the reference divides by a constant.
+__device__ __forceinline__ float div_const(float a, float c, float rc) {
+  const float q = __fmul_rn(a, rc);
+  const float r = __fmaf_rn(-q, c, a);
+  return __fmaf_rn(r, rc, q);
+}
+
 // Sample position along one axis for output pixel `pix` displaced by `disp`.
-//   grid  g = 2*(pix+disp)/(size-1) - 1         UnFlowLoss.py:16-19,30-31,89-91 (three separate
-//                                               fp32 roundings: separate torch kernels)
-//   TORCH p = ((g+1)*size - 1)/2                ATen grid_sampler_unnormalize(align_corners=False)
-//                                               (compiled with -fmad: one FMA)
-//   TRT   p = ((g+1)*(size-1))/2                trt_plugins/grid_sampler.cu:55-58
-//   border clip to [0,size-1]                   clip_coordinates; grid_sampler.cu:62-64
+//   grid  g = 2*(pix+disp)/(size-1) - 1     UnFlowLoss.py:16-19,30-31,89-91: three separate fp32
+//                                           roundings (separate torch kernels).  On CUDA -- the
+//                                           reference's training path -- ATen evaluates
+//                                           `tensor / python_scalar` as tensor * RN(1/scalar);
+//                                           its CPU kernels divide.  CERB_WARP_TORCH follows CUDA,
+//                                           CERB_WARP_TORCH_CPU the true division (the golden
+//                                           fixtures were generated on CPU).
+//   TORCH p = ((g+1)*size - 1)/2            ATen grid_sampler_unnormalize(align_corners=False)
+//   TRT   p = ((g+1)*(size-1))/2            trt_plugins/grid_sampler.cu:55-58
+//   border clip to [0,size-1]               clip_coordinates; grid_sampler.cu:62-64
 // inside = un-clipped position strictly inside (0,size-1) -> gradient passes (ATen
 // clip_coordinates_set_grad), else zero.
-__device__ __forceinline__ float sample_pos(int pix, float disp, int size, int mode, bool& inside) {
+__device__ __forceinline__ float sample_pos(int pix, float disp, int size, int mode, bool& inside, int unnorm_fma = 1) {
+  const float sm1 = (float)(size - 1);
+  const float rsm1 = __frcp_rn(sm1);
   float v = __fadd_rn((float)pix, disp);
   v = __fmul_rn(2.0f, v);
-  v = __fdiv_rn(v, (float)(size - 1));
+  v = (mode == CERB_WARP_TORCH) ? __fmul_rn(v, rsm1) : div_const(v, sm1, rsm1);
   const float g = __fadd_rn(v, -1.0f);
   float p;
   if (mode == CERB_WARP_TRT)
-    p = __fdiv_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)(size - 1)), 2.f);
+    p = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), sm1), 0.5f);  // (.)/2 is exact as *0.5
   else
-    p = __fdiv_rn(__fmaf_rn(__fadd_rn(g, 1.f), (float)size, -1.f), 2.f);
-  const float hi = (float)(size - 1);
+    p = unnorm_fma ? __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.f), (float)size, -1.f), 0.5f)
+                   : __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), -1.f), 0.5f);
+  const float hi = sm1;
   inside = (p > 0.f) && (p < hi);
   return fminf(hi, fmaxf(p, 0.f));
 }

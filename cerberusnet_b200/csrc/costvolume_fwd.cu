@@ -20,21 +20,38 @@
 // Generic path (any pad/kernel/stride parameters): one thread per output element.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
 #include "costvolume_common.cuh"
 #include "costvolume_launch.h"
 
 namespace cerb {
 
+static long long* g_trace_buffer = nullptr;  // debugging only
+void set_trace_buffer(long long* p) { g_trace_buffer = p; }
+#define CERB_TRACE(slot) do { if (a.dbg) a.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+
 // ------------------------------------------------------------------ configuration --------
 constexpr int kMD = 4;
 constexpr int kD = 2 * kMD + 1;  // 9
 constexpr int kD2 = kD * kD;     // 81
-constexpr int kProducerThreads = 96;
-constexpr int kCC = 8;      // channels per pipeline stage
-constexpr int kStages = 3;
+constexpr int kProducerThreads = 224;  // 7 staging warps (16 warps total = 4 per SMSP -> 128 regs)
+constexpr int kProducerWarps = kProducerThreads / 32;
+constexpr int kGatherWarps = kProducerWarps - 1;    // warp 0 of the staging warps only issues TMA
+constexpr int kGatherThreads = kGatherWarps * 32;
+constexpr int kStages = 3;     // x1 / warped-x2 stages
+constexpr int kRawMargin = 6;  // flow variation (px) inside one halo tile the raw box absorbs
+constexpr int kCBatch = 1;     // direct-gather fallback: channels per software-pipelined batch
 
-template <int TY, int TX, int KS>
+enum { PATH_TMA_X2 = 0, PATH_RAW = 1, PATH_DIRECT = 2 };
+
+// TY x TX output tile, KS-way in-CTA channel split, CC channels per pipeline stage, RS raw-box stages
+template <int TY, int TX, int KS, int CC_, int RS_>
 struct FwdCfg {
+  static constexpr int CC = CC_;   // channels per pipeline stage
+  static constexpr int RS = RS_;   // raw x2 source boxes (TMA) in flight
   static constexpr int NSTRIP = TX / 8;
   static constexpr int COMBOS = TY * kD;
   static constexpr int GROUP = NSTRIP * COMBOS;
@@ -43,18 +60,27 @@ struct FwdCfg {
   static constexpr int HY = TY + 2 * kMD, HX = TX + 2 * kMD;
   static constexpr int XS = HX + 4;  // 44 / 28: 8 consecutive rows hit 8 distinct 16-byte bank groups
   static constexpr int NPOS = HY * HX;
-  static constexpr int POS_PER_THREAD = (NPOS + kProducerThreads - 1) / kProducerThreads;
-  static constexpr int X1_STAGE = kCC * TY * TX;  // floats
-  static constexpr int X2_STAGE = kCC * HY * XS;  // floats
-  static constexpr int OUT_TILE = kD2 * TY * TX;  // floats, one partial buffer
+  static constexpr int POS_PER_THREAD = (NPOS + kGatherThreads - 1) / kGatherThreads;
+  // raw source box: halo + flow-variation margin both sides + the far bilinear tap + the
+  // (W/(W-1)) stretch of the training-path warp, and 3 columns so the box can start 16B-aligned
+  static constexpr int RAW_H = HY + 2 * kRawMargin + 2;
+  static constexpr int RAW_W = (HX + 2 * kRawMargin + 2 + 3 + 3) / 4 * 4;
+  static constexpr int X1_STAGE = CC * TY * TX;       // floats
+  static constexpr int X2_STAGE = CC * HY * XS;       // floats
+  static constexpr int RAW_STAGE = CC * RAW_H * RAW_W;  // floats
+  static constexpr int OUT_TILE = kD2 * TY * TX;       // floats, one partial buffer
   static constexpr size_t SMEM_X1 = 0;
   static constexpr size_t SMEM_X2 = SMEM_X1 + sizeof(float) * kStages * X1_STAGE;
-  static constexpr size_t SMEM_OUT = (SMEM_X2 + sizeof(float) * kStages * X2_STAGE + 1023) / 1024 * 1024;
-  static constexpr size_t SMEM_BAR = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
-  static constexpr size_t SMEM_BYTES = SMEM_BAR + 2 * kStages * sizeof(uint64_t) + 1024;  // + alignment slack
+  static constexpr size_t SMEM_RAW = (SMEM_X2 + sizeof(float) * kStages * X2_STAGE + 127) / 128 * 128;
+  static constexpr size_t SMEM_OUT = (SMEM_RAW + sizeof(float) * RS * RAW_STAGE + 1023) / 1024 * 1024;
+  static constexpr size_t SMEM_RED = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
+  static constexpr size_t SMEM_BAR = SMEM_RED + sizeof(int) * 2 * kProducerWarps * 4;  // (kGatherWarps rows used)
+  static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * kStages + 2 * RS) * sizeof(uint64_t) + 1024;
   static_assert(NCONS % 32 == 0, "consumer threads must be whole warps");
   static_assert((sizeof(float) * X1_STAGE) % 1024 == 0, "x1 stage must keep 1024-byte alignment");
-  static_assert(kCC % KS == 0, "channel groups must divide the stage");
+  static_assert((sizeof(float) * X2_STAGE) % 128 == 0 && (sizeof(float) * RAW_STAGE) % 128 == 0, "TMA dst alignment");
+  static_assert(CC % KS == 0, "channel groups must divide the stage");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 // (y, dy) enumeration per strip: aligned lane pairs share the x2 row r = y + dy wherever possible.
@@ -97,8 +123,12 @@ struct FwdArgs {
   void* out;
   int off;        // md - pad: output pixel (by,bx) looks at input pixel (by+off, bx+off)
   int tiles_x, tiles_y, total_tiles;
-  int nchunks;    // ceil(C / kCC)
-  int use_tma_in, use_tma_out;
+  int nchunks;    // ceil(C / CC)
+  int use_tma_in;   // x1 tiles by TMA
+  int use_tma_x2;   // un-warped x2 halo tiles by TMA (flow == null)
+  int use_tma_raw;  // raw x2 source boxes by TMA, warp gathered from shared memory
+  int use_tma_out;  // output tile by TMA store
+  long long* dbg;   // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 64 slots per CTA
 };
 
 // 16-byte chunk swizzle of a [rows][TX] fp32 tile: CU_TENSOR_MAP_SWIZZLE_128B for TX == 32
@@ -110,19 +140,24 @@ __device__ __forceinline__ int swz_chunk(int row, int chunk) {
 }
 
 // ------------------------------------------------------------------ fast kernel ----------
-template <typename T, int TY, int TX, int KS>
-__global__ void __launch_bounds__(FwdCfg<TY, TX, KS>::NTHREADS, 1)
-warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_out) {
-  using Cfg = FwdCfg<TY, TX, KS>;
+template <typename T, int TY, int TX, int KS, int CC, int RS>
+__global__ void __launch_bounds__(FwdCfg<TY, TX, KS, CC, RS>::NTHREADS, 1)
+warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
+                     const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_out) {
+  using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // keep the pointer derived from smem_raw (so loads/stores stay LDS/STS) while forcing the
   // 1024-byte alignment the 128B TMA swizzle atoms need
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* x1s = (float*)(smem + Cfg::SMEM_X1);
   float* x2s = (float*)(smem + Cfg::SMEM_X2);
+  float* raws = (float*)(smem + Cfg::SMEM_RAW);
   float* outs = (float*)(smem + Cfg::SMEM_OUT);
+  int* red = (int*)(smem + Cfg::SMEM_RED);
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::SMEM_BAR);
   uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* raw_full = empty_bar + kStages;
+  uint64_t* raw_empty = raw_full + RS;
 
   const Geom& g = a.g;
   const int tid = threadIdx.x;
@@ -131,116 +166,309 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1 + kProducerThreads / 32);
+      mbar_init(&full_bar[s], 1 + kGatherWarps);  // TMA thread (+tx bytes) and one arrival per gather warp
       mbar_init(&empty_bar[s], Cfg::NCONS / 32);
+    }
+    for (int s = 0; s < RS; ++s) {
+      mbar_init(&raw_full[s], 1);
+      mbar_init(&raw_empty[s], kGatherWarps);
     }
     fence_barrier_init();
     if (a.use_tma_in) tma_prefetch_desc(&tm_x1);
+    if (a.use_tma_x2) tma_prefetch_desc(&tm_x2);
+    if (a.use_tma_raw) tma_prefetch_desc(&tm_raw);
     if (a.use_tma_out) tma_prefetch_desc(&tm_out);
   }
   __syncthreads();
+  if (tid == 0) CERB_TRACE(0);
 
   int stage = 0;
   uint32_t phase = 0;
 
   if (tid >= Cfg::NCONS) {
-    // =========================== PRODUCER WARPS ===========================
+    // =========================== STAGING WARPS ===========================
+    // producer warp 0: one elected lane issues every TMA copy (a TMA issue blocks the issuing
+    // thread for hundreds of cycles, so it must not share a warp with the gather);
+    // producer warps 1..6: bilinear gather of the warped x2 halo tile.
     const int pt = tid - Cfg::NCONS;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-      const int n = tile / (a.tiles_x * a.tiles_y);
-      const int trem = tile - n * (a.tiles_x * a.tiles_y);
-      const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
-      // input-frame origin of the x1 tile and of the x2 halo tile
-      const int iy0 = by0 + a.off, ix0 = bx0 + a.off;
-      const int qy0 = iy0 - kMD, qx0 = ix0 - kMD;
+    const int pwarp = pt >> 5;
+    const int lane = pt & 31;
+    const bool warped = a.flow != nullptr;
+    const bool reduce_bbox = warped && a.use_tma_raw;
+    int red_par = 0;
 
-      // per-position sampling data, fixed for the whole tile (all channels reuse it)
-      Taps taps[Cfg::POS_PER_THREAD];
-      int sdst[Cfg::POS_PER_THREAD];  // smem float offset inside a channel plane, -1 = no position
-      unsigned valid_mask = 0;
+    if (pwarp == 0) {
+      // ---------------------------- TMA warp ----------------------------
+      int ri = 0, xs = 0;
+      uint32_t riphase = 0, xphase = 0;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n = tile / (a.tiles_x * a.tiles_y);
+        const int trem = tile - n * (a.tiles_x * a.tiles_y);
+        const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
+        const int iy0 = by0 + a.off, ix0 = bx0 + a.off;
+        const int qy0 = iy0 - kMD, qx0 = ix0 - kMD;
+        int path = (!warped && a.use_tma_x2) ? PATH_TMA_X2 : PATH_DIRECT, ox = 0, oy = 0;
+        // x1 does not depend on the flow: request the first stages' tiles while the gather warps
+        // are still computing sample positions and the bounding box
+        int x1_pre = 0;
+        if (reduce_bbox && a.use_tma_in && lane == 0) {
+          for (; x1_pre < kStages && x1_pre < a.nchunks; ++x1_pre) {
+            mbar_wait(&empty_bar[xs], xphase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[xs], (uint32_t)(sizeof(float) * Cfg::X1_STAGE));
+            tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, x1_pre * CC, n);
+            if (++xs == kStages) { xs = 0; xphase ^= 1; }
+          }
+        }
+        if (reduce_bbox) {
+          named_bar_sync(2, kProducerThreads);
+          const int* rp = red + red_par * (kGatherWarps * 4);
+          int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
 #pragma unroll
-      for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
-        const int i = pt + j * kProducerThreads;
-        sdst[j] = -1;
-        if (i < Cfg::NPOS) {
-          const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
-          sdst[j] = hy * Cfg::XS + hx;
-          const int qy = qy0 + hy, qx = qx0 + hx;
-          if (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) {
-            valid_mask |= 1u << j;
-            if (a.flow != nullptr) {
-              const float* fp = a.flow + (long long)n * g.fls[0] + (long long)qy * g.fls[2] + qx;
-              const float u = __ldg(fp), v = __ldg(fp + g.fls[1]);
-              bool in_x, in_y;
-              const float sx = sample_pos(qx, u, g.W, g.warp_mode, in_x);
-              const float sy = sample_pos(qy, v, g.H, g.warp_mode, in_y);
-              taps[j] = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
-            } else {
-              const int o = (int)(qy * g.x2s[2]) + qx;
-              taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = o;
-              taps[j].w[0] = 1.f; taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
+          for (int w = 0; w < kGatherWarps; ++w) {
+            xmin = min(xmin, rp[w * 4 + 0]); xmax = max(xmax, rp[w * 4 + 1]);
+            ymin = min(ymin, rp[w * 4 + 2]); ymax = max(ymax, rp[w * 4 + 3]);
+          }
+          red_par ^= 1;
+          ox = xmin & ~3;
+          oy = ymin;
+          if (xmin <= xmax && xmax - ox < Cfg::RAW_W && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+        }
+        if (lane == 0) {
+          for (int ck = 0; ck < a.nchunks; ++ck) {
+            if (path == PATH_RAW) {
+              mbar_wait(&raw_empty[ri], riphase ^ 1);
+              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
+              tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
+              if (++ri == RS) { ri = 0; riphase ^= 1; }
             }
+            if (ck < x1_pre) continue;  // x1 tile already requested above
+            mbar_wait(&empty_bar[xs], xphase ^ 1);
+            const uint32_t tx = (a.use_tma_in ? (uint32_t)(sizeof(float) * Cfg::X1_STAGE) : 0u) +
+                                (path == PATH_TMA_X2 ? (uint32_t)(sizeof(float) * Cfg::X2_STAGE) : 0u);
+            if (tx) mbar_arrive_expect_tx(&full_bar[xs], tx);
+            else mbar_arrive(&full_bar[xs]);
+            if (a.use_tma_in) tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, ck * CC, n);
+            if (path == PATH_TMA_X2) tma_load_4d(x2s + xs * Cfg::X2_STAGE, &tm_x2, &full_bar[xs], qx0, qy0, ck * CC, n);
+            if (++xs == kStages) { xs = 0; xphase ^= 1; }
+            if (ck < 8) CERB_TRACE(2 + ck);
           }
-        }
-      }
-
-      for (int ck = 0; ck < a.nchunks; ++ck) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        float* x1dst = x1s + stage * Cfg::X1_STAGE;
-        float* x2dst = x2s + stage * Cfg::X2_STAGE;
-        const int c0 = ck * kCC;
-        if (pt == 0) {
-          if (a.use_tma_in) {
-            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(sizeof(float) * Cfg::X1_STAGE));
-            tma_load_4d(x1dst, &tm_x1, &full_bar[stage], ix0, iy0, c0, n);
-          } else {
-            mbar_arrive(&full_bar[stage]);
-          }
-        }
-        if (!a.use_tma_in) {
-          // cooperative x1 tile load (any dtype / alignment), same swizzled layout TMA produces
-          for (int e = pt; e < Cfg::X1_STAGE; e += kProducerThreads) {
-            const int c = e / (TY * TX), rem = e - c * (TY * TX);
-            const int y = rem / TX, x = rem - y * TX;
-            const int iy = iy0 + y, ix = ix0 + x, ch = c0 + c;
-            float v = 0.f;
-            if (ch < g.C && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
-              v = ldg_f32(x1 + (long long)n * g.x1s[0] + (long long)ch * g.x1s[1] + (long long)iy * g.x1s[2] + ix);
-            const int row = c * TY + y;
-            x1dst[row * TX + swz_chunk<TX>(row, x >> 2) * 4 + (x & 3)] = v;
-          }
-        }
-        // warped (or plain) x2 halo tile for this channel chunk
-        const T* x2n = x2 + (long long)n * g.x2s[0];
-#pragma unroll 2
-        for (int c = 0; c < kCC; ++c) {
-          const int ch = c0 + c;
-          const T* plane = x2n + (long long)ch * g.x2s[1];
-          const bool ch_ok = ch < g.C;
-          float vals[Cfg::POS_PER_THREAD];
-#pragma unroll
-          for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
-            float v = 0.f;
-            if (ch_ok && ((valid_mask >> j) & 1u)) {
-              if (a.flow != nullptr) {
-                const float v0 = ldg_f32(plane + taps[j].off[0]);
-                const float v1 = ldg_f32(plane + taps[j].off[1]);
-                const float v2 = ldg_f32(plane + taps[j].off[2]);
-                const float v3 = ldg_f32(plane + taps[j].off[3]);
-                v = blend(v0, v1, v2, v3, taps[j]);
-              } else {
-                v = ldg_f32(plane + taps[j].off[0]);
-              }
-            }
-            vals[j] = v;
-          }
-#pragma unroll
-          for (int j = 0; j < Cfg::POS_PER_THREAD; ++j)
-            if (sdst[j] >= 0) x2dst[c * (Cfg::HY * Cfg::XS) + sdst[j]] = vals[j];
         }
         __syncwarp();
-        if ((pt & 31) == 0) mbar_arrive(&full_bar[stage]);
+      }
+    } else {
+      // ---------------------------- gather warps ----------------------------
+      const int gt = pt - 32;  // 0 .. kGatherThreads-1
+      int rc = 0;
+      uint32_t rcphase = 0;
+
+      // x1 tile without TMA (any dtype / alignment): cooperative loads into the swizzled layout
+      auto coop_x1 = [&](float* x1dst, int ix0, int iy0, int c0, int n) {
+        constexpr int PER = (Cfg::X1_STAGE + kGatherThreads - 1) / kGatherThreads;
+        float v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int e = gt + k * kGatherThreads;
+          const int c = e / (TY * TX), rem = e - c * (TY * TX);
+          const int y = rem / TX, x = rem - y * TX;
+          const int iy = iy0 + y, ix = ix0 + x, ch = c0 + c;
+          v[k] = 0.f;
+          if (e < Cfg::X1_STAGE && ch < g.C && iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+            v[k] = ldg_f32(x1 + (long long)n * g.x1s[0] + (long long)ch * g.x1s[1] + (long long)iy * g.x1s[2] + ix);
+        }
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+          const int e = gt + k * kGatherThreads;
+          if (e < Cfg::X1_STAGE) {
+            const int c = e / (TY * TX), rem = e - c * (TY * TX);
+            const int y = rem / TX, x = rem - y * TX;
+            const int row = c * TY + y;
+            x1dst[row * TX + swz_chunk<TX>(row, x >> 2) * 4 + (x & 3)] = v[k];
+          }
+        }
+      };
+      auto publish_stage = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[stage]);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
+      };
+
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int n = tile / (a.tiles_x * a.tiles_y);
+        const int trem = tile - n * (a.tiles_x * a.tiles_y);
+        const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
+        // input-frame origin of the x1 tile and of the x2 halo tile
+        const int iy0 = by0 + a.off, ix0 = bx0 + a.off;
+        const int qy0 = iy0 - kMD, qx0 = ix0 - kMD;
+
+        // ------------- un-warped second map: the TMA warp loads the halo tile as a box -------------
+        if (!warped && a.use_tma_x2) {
+          for (int ck = 0; ck < a.nchunks; ++ck) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
+            publish_stage();
+          }
+          continue;
+        }
+
+        // ------------- per-position sampling data, fixed for the whole tile -------------
+        Taps taps[Cfg::POS_PER_THREAD];   // off[] first holds {x0, x1c, y0, y1c}, then offsets
+        int sdst[Cfg::POS_PER_THREAD];    // smem float offset inside a channel plane, -1 = no position
+        unsigned valid_mask = 0;
+        int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+#pragma unroll
+        for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+          const int i = gt + j * kGatherThreads;
+          sdst[j] = -1;
+          taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = 0;
+          taps[j].w[0] = taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
+          if (i < Cfg::NPOS) {
+            const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
+            sdst[j] = hy * Cfg::XS + hx;
+            const int qy = qy0 + hy, qx = qx0 + hx;
+            if (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) {
+              valid_mask |= 1u << j;
+              if (warped) {
+                const float* fp = a.flow + (long long)n * g.fls[0] + (long long)qy * g.fls[2] + qx;
+                const float u = __ldg(fp), v = __ldg(fp + g.fls[1]);
+                bool in_x, in_y;
+                const float sx = sample_pos(qx, u, g.W, g.warp_mode, in_x);
+                const float sy = sample_pos(qy, v, g.H, g.warp_mode, in_y);
+                taps[j] = make_taps(sx, sy, g.H, g.W, 0);  // hstride 0: off[] = {x0, x1c, x0, x1c}
+                const int y0 = (int)floorf(sy);
+                const int y1c = (y0 + 1 < g.H) ? y0 + 1 : y0;
+                taps[j].off[2] = y0;
+                taps[j].off[3] = y1c;
+              } else {
+                taps[j].off[0] = taps[j].off[1] = qx;
+                taps[j].off[2] = taps[j].off[3] = qy;
+                taps[j].w[0] = 1.f;
+              }
+              xmin = min(xmin, taps[j].off[0]); xmax = max(xmax, taps[j].off[1]);
+              ymin = min(ymin, taps[j].off[2]); ymax = max(ymax, taps[j].off[3]);
+            }
+          }
+        }
+        if (gt == 0) CERB_TRACE(58);
+
+        // ------------- does the tile's sampling footprint fit the raw TMA box? -------------
+        int path = PATH_DIRECT, ox = 0, oy = 0;
+        if (reduce_bbox) {
+          xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+          ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+          int* rp = red + red_par * (kGatherWarps * 4);
+          if (lane == 0) {
+            rp[(pwarp - 1) * 4 + 0] = xmin; rp[(pwarp - 1) * 4 + 1] = xmax;
+            rp[(pwarp - 1) * 4 + 2] = ymin; rp[(pwarp - 1) * 4 + 3] = ymax;
+          }
+          named_bar_sync(2, kProducerThreads);
+#pragma unroll
+          for (int w = 0; w < kGatherWarps; ++w) {
+            xmin = min(xmin, rp[w * 4 + 0]); xmax = max(xmax, rp[w * 4 + 1]);
+            ymin = min(ymin, rp[w * 4 + 2]); ymax = max(ymax, rp[w * 4 + 3]);
+          }
+          red_par ^= 1;
+          ox = xmin & ~3;  // TMA box starts must be 16-byte aligned
+          oy = ymin;
+          if (xmin <= xmax && xmax - ox < Cfg::RAW_W && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+        }
+#pragma unroll
+        for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+          const int x0 = taps[j].off[0], x1c = taps[j].off[1], y0 = taps[j].off[2], y1c = taps[j].off[3];
+          int r0, r1;
+          if (path == PATH_RAW) { r0 = (y0 - oy) * Cfg::RAW_W - ox; r1 = (y1c - oy) * Cfg::RAW_W - ox; }
+          else { r0 = (int)(y0 * g.x2s[2]); r1 = (int)(y1c * g.x2s[2]); }
+          taps[j].off[0] = r0 + x0; taps[j].off[1] = r0 + x1c; taps[j].off[2] = r1 + x0; taps[j].off[3] = r1 + x1c;
+        }
+        if (gt == 0) CERB_TRACE(1);
+
+        if (path == PATH_RAW) {
+          // ------------- warp gathered from the raw source box in shared memory -------------
+          for (int ck = 0; ck < a.nchunks; ++ck) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
+            if (gt == 0 && ck < 4) CERB_TRACE(44 + 3 * ck);
+            mbar_wait(&raw_full[rc], rcphase);
+            if (gt == 0 && ck < 4) CERB_TRACE(45 + 3 * ck);
+            const float* __restrict__ src = raws + rc * Cfg::RAW_STAGE;
+            float* __restrict__ x2dst = x2s + stage * Cfg::X2_STAGE;
+            // all taps of one channel are loaded before any result is stored: the loads of the
+            // POS_PER_THREAD samples overlap instead of serialising behind the stores
+#pragma unroll
+            for (int c = 0; c < CC; ++c) {
+              const float* __restrict__ sp = src + c * (Cfg::RAW_H * Cfg::RAW_W);
+              float* __restrict__ dp = x2dst + c * (Cfg::HY * Cfg::XS);
+              float tv[Cfg::POS_PER_THREAD][4];
+#pragma unroll
+              for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tv[j][k] = sp[taps[j].off[k]];  // off = 0 for invalid positions
+              }
+#pragma unroll
+              for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+                const float r = ((valid_mask >> j) & 1u) ? blend(tv[j][0], tv[j][1], tv[j][2], tv[j][3], taps[j]) : 0.f;
+                if (sdst[j] >= 0) dp[sdst[j]] = r;
+              }
+            }
+            __syncwarp();
+            if (gt == 0 && ck < 4) CERB_TRACE(46 + 3 * ck);
+            if (lane == 0) mbar_arrive(&raw_empty[rc]);
+            if (++rc == RS) { rc = 0; rcphase ^= 1; }
+            publish_stage();
+          }
+          continue;
+        }
+
+        // ------------- fallback: gather straight from global memory (any dtype / alignment / flow) -------------
+        // The loads of batch gb+1 are issued before batch gb is blended and stored, and they run
+        // ahead across chunk boundaries -- only the shared-memory stores wait for a free stage.
+        constexpr int NB = CC / kCBatch;
+        constexpr int NV = Cfg::POS_PER_THREAD * kCBatch * 4;
+        const T* x2n = x2 + (long long)n * g.x2s[0];
+        const int total_batches = a.nchunks * NB;
+        float cur[NV], nxt[NV];
+        auto issue = [&](int gb, float (&dst)[NV]) {
+          const int chb = gb * kCBatch;
+#pragma unroll
+          for (int cb = 0; cb < kCBatch; ++cb) {
+            const int ch = chb + cb;
+            const T* plane = x2n + (long long)ch * g.x2s[1];
+            const bool ch_ok = ch < g.C;
+#pragma unroll
+            for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+              const bool ok = ch_ok && ((valid_mask >> j) & 1u);
+              float* d = &dst[(cb * Cfg::POS_PER_THREAD + j) * 4];
+              d[0] = ok ? ldg_f32(plane + taps[j].off[0]) : 0.f;
+              if (warped) {
+                d[1] = ok ? ldg_f32(plane + taps[j].off[1]) : 0.f;
+                d[2] = ok ? ldg_f32(plane + taps[j].off[2]) : 0.f;
+                d[3] = ok ? ldg_f32(plane + taps[j].off[3]) : 0.f;
+              }
+            }
+          }
+        };
+        issue(0, cur);
+        for (int gb = 0; gb < total_batches; ++gb) {
+          if (gb + 1 < total_batches) issue(gb + 1, nxt);
+          const int ck = gb / NB, bi = gb - ck * NB;
+          float* x2dst = x2s + stage * Cfg::X2_STAGE;
+          if (bi == 0) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
+          }
+#pragma unroll
+          for (int cb = 0; cb < kCBatch; ++cb) {
+            float* plane_dst = x2dst + (bi * kCBatch + cb) * (Cfg::HY * Cfg::XS);
+#pragma unroll
+            for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+              const float* v = &cur[(cb * Cfg::POS_PER_THREAD + j) * 4];
+              const float r = warped ? blend(v[0], v[1], v[2], v[3], taps[j]) : v[0];
+              if (sdst[j] >= 0) plane_dst[sdst[j]] = r;
+            }
+          }
+          if (bi == NB - 1) publish_stage();
+#pragma unroll
+          for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+        }
       }
     }
   } else {
@@ -250,7 +478,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const int strip = u / Cfg::COMBOS;
     int y, dyi;
     combo_of<TY>(u - strip * Cfg::COMBOS, y, dyi);
-    const float inv_div = (float)g.C;  // k == 1: nelems = C (correlation_cuda_kernel.cu:85)
+    const float divisor = (float)g.C;  // k == 1: nelems = C (correlation_cuda_kernel.cu:85)
+    const float rdivisor = __frcp_rn(divisor);
 
     // shared-memory float offsets that do not depend on stage / channel
     const int x2_off = (y + dyi) * Cfg::XS + strip * 8;
@@ -258,6 +487,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
     for (int h = 0; h < 2; ++h) x1_off[h] = y * TX + swz_chunk<TX>(y, strip * 2 + h) * 4;  // row = c*TY + y; TY % 8 == 0 or TX < 32
 
+    if (tid == 0) CERB_TRACE(16);
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       const int n = tile / (a.tiles_x * a.tiles_y);
       const int trem = tile - n * (a.tiles_x * a.tiles_y);
@@ -269,10 +499,11 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
       for (int ck = 0; ck < a.nchunks; ++ck) {
         mbar_wait(&full_bar[stage], phase);
+        if (tid == 0 && ck < 8) CERB_TRACE(17 + 2 * ck);
         const float* x1p = x1s + stage * Cfg::X1_STAGE;
         const float* x2p = x2s + stage * Cfg::X2_STAGE + x2_off;
 #pragma unroll
-        for (int cc = 0; cc < kCC / KS; ++cc) {
+        for (int cc = 0; cc < CC / KS; ++cc) {
           const int c = cc * KS + grp;
           float av[8], bv[16];
 #pragma unroll
@@ -294,8 +525,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
+        if (tid == 0 && ck < 8) CERB_TRACE(18 + 2 * ck);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      if (tid == 0) CERB_TRACE(40);
 
       // ---------------- epilogue: /C, LeakyReLU, stage tile, TMA store ----------------
       if (a.use_tma_out) {
@@ -314,7 +547,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           for (int e = 0; e < 4; ++e) {
             float r = acc[(4 * h + e) * kD + dx];
             if constexpr (KS == 1) {
-              r = __fdiv_rn(r, inv_div);
+              r = div_const(r, divisor, rdivisor);
               if (g.has_act) r = leaky(r, g.slope);
             }
             vv[e] = r;
@@ -328,7 +561,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           float s = outs[e];
 #pragma unroll
           for (int k2 = 1; k2 < KS; ++k2) s += outs[k2 * Cfg::OUT_TILE + e];
-          s = __fdiv_rn(s, inv_div);
+          s = div_const(s, divisor, rdivisor);
           if (g.has_act) s = leaky(s, g.slope);
           outs[e] = s;
         }
@@ -337,6 +570,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         fence_proxy_async_smem();
         named_bar_sync(1, Cfg::NCONS);
         if (tid == 0) {
+          CERB_TRACE(41);
           tma_store_4d(&tm_out, outs, bx0, by0, 0, n);
           tma_store_commit();
         }
@@ -355,7 +589,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         named_bar_sync(1, Cfg::NCONS);  // `outs` is rewritten by the next tile's epilogue
       }
     }
-    if (a.use_tma_out && tid == 0) tma_store_wait_all0();
+    // the tile buffer only has to outlive the store's shared-memory reads; the writes are
+    // complete at kernel end like any other store
+    if (a.use_tma_out && tid == 0) tma_store_wait_read0();
+    if (tid == 0) CERB_TRACE(42);
   }
 }
 
@@ -458,10 +695,10 @@ static int num_sms() {
   return n;
 }
 
-template <typename T, int TY, int TX, int KS>
+template <typename T, int TY, int TX, int KS, int CC, int RS>
 static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
                                int force_no_tma, cudaStream_t stream) {
-  using Cfg = FwdCfg<TY, TX, KS>;
+  using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
   FwdArgs a;
   a.g = g;
   a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out;
@@ -469,17 +706,30 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   a.tiles_x = (g.outW + TX - 1) / TX;
   a.tiles_y = (g.outH + TY - 1) / TY;
   a.total_tiles = g.B * a.tiles_x * a.tiles_y;
-  a.nchunks = (g.C + kCC - 1) / kCC;
-  CUtensorMap tm_x1, tm_out;
+  a.nchunks = (g.C + CC - 1) / CC;
+  a.dbg = g_trace_buffer;
+  CUtensorMap tm_x1, tm_x2, tm_raw, tm_out;
   memset(&tm_x1, 0, sizeof(tm_x1));
+  memset(&tm_x2, 0, sizeof(tm_x2));
+  memset(&tm_raw, 0, sizeof(tm_raw));
   memset(&tm_out, 0, sizeof(tm_out));
-  a.use_tma_in = 0;
-  a.use_tma_out = 0;
+  a.use_tma_in = a.use_tma_x2 = a.use_tma_raw = a.use_tma_out = 0;
+  int tma_mask = 15;  // debugging knob CERB_DEBUG_TMA: bit0 x1 loads, bit1 stores, bit2 plain x2 tiles, bit3 raw x2 boxes
+  if (const char* e = getenv("CERB_DEBUG_TMA")) tma_mask = atoi(e);
   if (std::is_same<T, float>::value && !force_no_tma) {
-    a.use_tma_in = make_tmap_f32(&tm_x1, x1, g.W, g.H, g.C, g.B, g.x1s, TX, TY, kCC, TX == 32) ? 1 : 0;
-    a.use_tma_out = make_tmap_f32(&tm_out, out, g.outW, g.outH, g.D2, g.B, g.os, TX, TY, kD2, TX == 32) ? 1 : 0;
+    // the box start of a TMA tile load must be 16-byte aligned in global memory (misaligned
+    // starts trap): x1 / x2 tiles begin at bx0 + (md - pad) (- 4), so pad != md (mod 4) stages
+    // them with LDG instead.  Raw boxes are aligned by construction.
+    if ((tma_mask & 1) && (a.off % 4) == 0)
+      a.use_tma_in = make_tmap_f32(&tm_x1, x1, g.W, g.H, g.C, g.B, g.x1s, TX, TY, CC, TX == 32) ? 1 : 0;
+    if ((tma_mask & 4) && (a.off % 4) == 0 && flow == nullptr)
+      a.use_tma_x2 = make_tmap_f32(&tm_x2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::XS, Cfg::HY, CC, false) ? 1 : 0;
+    if ((tma_mask & 8) && flow != nullptr)
+      a.use_tma_raw = make_tmap_f32(&tm_raw, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W, Cfg::RAW_H, CC, false) ? 1 : 0;
+    if (tma_mask & 2)
+      a.use_tma_out = make_tmap_f32(&tm_out, out, g.outW, g.outH, g.D2, g.B, g.os, TX, TY, kD2, TX == 32) ? 1 : 0;
   }
-  auto kern = warp_corr_fwd_kernel<T, TY, TX, KS>;
+  auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS>;
   static bool attr_set = false;  // benign race: the attribute call is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -487,7 +737,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
     attr_set = true;
   }
   const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(a, tm_x1, tm_out);
+  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(a, tm_x1, tm_x2, tm_raw, tm_out);
   return cudaGetLastError();
 }
 
@@ -503,8 +753,8 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
       const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8);
       small = big_tiles < (long long)num_sms() * 3 / 4;
     }
-    if (small) return launch_fast<T, 4, 16, 4>(g, x1, x2, flow, out, no_tma, stream);
-    return launch_fast<T, 8, 32, 1>(g, x1, x2, flow, out, no_tma, stream);
+    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, stream);
+    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, stream);
   }
   const long long total = (long long)g.B * g.D2 * g.outH * g.outW;
   long long blocks = (total + 255) / 256;

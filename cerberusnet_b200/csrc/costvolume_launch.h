@@ -32,5 +32,6 @@ cudaError_t launch_flow_warp_backward(int dtype, const void* image, const float*
                                       float* gflow, int B, int C, int H, int W, int mode, cudaStream_t stream);
 
 void count_launches(int n);
+void set_trace_buffer(long long* p);
 
 }  // namespace cerb

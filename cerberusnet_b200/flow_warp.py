@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import WARP_TORCH, WARP_TRT
+from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT
 
 __all__ = ["flow_warp", "FlowWarpFunction", "mesh_grid", "norm_grid"]
 

@@ -11,11 +11,11 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TRT, CostVolumeError, check, current_stream_ptr, lib, make_params,
+from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, check, current_stream_ptr, lib, make_params,
                    output_dims, ptr, require_cuda)
 
 __all__ = ["warp_corr_forward", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
-           "WARP_TORCH", "WARP_TRT"]
+           "WARP_TORCH", "WARP_TRT", "WARP_TORCH_CPU"]
 
 
 def _inner_contig(t: torch.Tensor) -> torch.Tensor:

@@ -46,8 +46,12 @@ enum { CERB_F32 = 0, CERB_F16 = 1, CERB_BF16 = 2 };
 
 /* flow-warp conventions of the second feature map */
 enum {
-  CERB_WARP_TORCH = 0, /* nnet_training/loss_functions/UnFlowLoss.py:83-94 (ATen grid_sample) */
-  CERB_WARP_TRT = 1    /* runtime/cerberus_net/trt_plugins/grid_sampler.cu:48-59 */
+  CERB_WARP_TORCH = 0,    /* nnet_training/loss_functions/UnFlowLoss.py:83-94 as it runs on CUDA (the
+                             reference's training path): ATen evaluates `grid / (size-1)` as a
+                             multiplication by the rounded reciprocal there */
+  CERB_WARP_TRT = 1,      /* runtime/cerberus_net/trt_plugins/grid_sampler.cu:48-59 */
+  CERB_WARP_TORCH_CPU = 2 /* same as TORCH but with the true division ATen's CPU kernels perform
+                             (1 ulp apart in the grid; lets CPU-generated fixtures be matched) */
 };
 
 /* argument errors (negative so they never collide with cudaError_t) */

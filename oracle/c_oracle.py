@@ -15,8 +15,9 @@ _LIB_PATH = os.path.join(_HERE, "libcostvolume_oracle.so")
 
 ACC_REFERENCE_ORDER = 0
 ACC_DOUBLE = 1
-WARP_TORCH = 0
+WARP_TORCH = 0      # ATen CUDA flavour (grid / (size-1) as reciprocal multiply): the reference's training path
 WARP_TRT = 1
+WARP_TORCH_CPU = 2  # ATen CPU flavour (true division): what the golden fixtures were generated with
 
 _f32p = ctypes.POINTER(ctypes.c_float)
 _lib = None

@@ -19,8 +19,9 @@ from typing import Optional
 import torch
 import torch.nn.functional as F
 
-WARP_TORCH = 0
+WARP_TORCH = 0      # whatever ATen does on the tensor's device (CUDA: reciprocal multiply, CPU: division)
 WARP_TRT = 1
+WARP_TORCH_CPU = 2  # alias of WARP_TORCH for CPU tensors
 
 
 def corr_out_dims(H: int, W: int, pad: int, k: int, md: int, s1: int, s2: int):
@@ -90,7 +91,7 @@ def flow_warp(image: torch.Tensor, flow12: torch.Tensor, mode: int = WARP_TORCH)
     pos = pixel_grid(B, H, W, image) + flow12
     gx = 2.0 * pos[:, 0] / (W - 1) - 1.0
     gy = 2.0 * pos[:, 1] / (H - 1) - 1.0
-    if mode == WARP_TORCH:
+    if mode in (WARP_TORCH, WARP_TORCH_CPU):
         grid = torch.stack([gx, gy], dim=-1)
         return F.grid_sample(image, grid, mode="bilinear", padding_mode="border", align_corners=False)
     ix = ((gx + 1.0) * (W - 1)) / 2.0

@@ -1,0 +1,386 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes) / the reference-shaped
+Python surfaces, against the CPU oracle and the golden vectors on the same seeded inputs.
+
+Tolerances (stated per SURVEY.md 8d / north_star: 1e-5 relative, fp32):
+  fp32   max|diff| <= 1e-5 * max|ref|         (measured ~3e-7: summation order only)
+  fp16   max|diff| <= 2e-3 * max|ref|         (one half-precision rounding of the output)
+  bf16   max|diff| <= 1.6e-2 * max|ref|
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cerberusnet_b200 as cb
+from cerberusnet_b200 import _lib, ops
+from conftest import rel_err
+from make_golden import CASES, golden_inputs
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+VARIANTS = [0, 1, 2, 3, 4, 5]
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def to_dev(*arrs):
+    return [None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev()) for a in arrs]
+
+
+def rand_case(seed, B, C, H, W, sigma=2.5):
+    rs = np.random.RandomState(seed)
+    return (rs.standard_normal((B, C, H, W)).astype(np.float32), rs.standard_normal((B, C, H, W)).astype(np.float32),
+            (rs.standard_normal((B, 2, H, W)) * sigma).astype(np.float32))
+
+
+# ------------------------------------------------------------------ golden vectors
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("corr_")])
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_correlation_vs_reference_golden(golden_dir, name, variant):
+    x1, x2, _ = golden_inputs(name)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    t1, t2 = to_dev(x1, x2)
+    out = ops.warp_corr_forward(t1, t2, None, 4, 1, 4, 1, 1, variant=variant).cpu().numpy()
+    if name == "corr_config1":  # BASELINE.json configs[0]
+        assert rel_err(out[:, :, ::4, ::4], gold["out_sub4"]) < TOL
+        assert rel_err(out.astype(np.float64).sum(axis=(2, 3)), gold["plane_sums_f64"]) < TOL
+    else:
+        assert rel_err(out, gold["out"]) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("level_")])
+def test_fused_level_vs_reference_golden(golden_dir, name):
+    x1, x2, flow = golden_inputs(name)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    t1, t2, tf = to_dev(x1, x2, flow)
+    for t in (t1, t2, tf):
+        t.requires_grad_()
+    out = cb.warp_correlation(t1, t2, tf, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH_CPU, 0.1)  # fixtures: ATen CPU grid
+    assert rel_err(out.detach().cpu().numpy(), gold["out"]) < TOL
+    g = np.random.RandomState(1000 + CASES[name][0]).standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).to(dev()))
+    assert rel_err(t1.grad.cpu().numpy(), gold["grad_x1"]) < TOL
+    assert rel_err(t2.grad.cpu().numpy(), gold["grad_x2"]) < TOL
+    assert rel_err(tf.grad.cpu().numpy(), gold["grad_flow"]) < TOL
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("warp_")])
+def test_flow_warp_vs_reference_golden(golden_dir, name):
+    img, _, flow = golden_inputs(name)
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    ti, tf = to_dev(img, flow)
+    ti.requires_grad_()
+    tf.requires_grad_()
+    out = cb.flow_warp(ti, tf, warp_mode=cb.WARP_TORCH_CPU)  # fixtures: ATen CPU grid
+    assert rel_err(out.detach().cpu().numpy(), gold["out"]) < TOL
+    g = np.random.RandomState(1000 + CASES[name][0]).standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(torch.from_numpy(g).to(dev()))
+    assert rel_err(ti.grad.cpu().numpy(), gold["grad_image"]) < TOL
+    assert rel_err(tf.grad.cpu().numpy(), gold["grad_flow"]) < TOL
+
+
+# ------------------------------------------------------------------ oracle sweeps
+SHAPES = [(1, 32, 16, 32), (2, 20, 13, 37), (1, 192, 8, 16), (3, 7, 9, 50), (1, 48, 24, 64), (1, 8, 3, 5), (2, 1, 40, 8)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("mode", [None, cb.WARP_TORCH, cb.WARP_TRT, cb.WARP_TORCH_CPU])
+def test_forward_variants_vs_oracle(shape, variant, mode):
+    """Ragged sizes: W not a multiple of 4 (no TMA), C not a multiple of the 8-channel stage,
+    images smaller than one tile, batch > 1."""
+    x1, x2, fl = rand_case(hash(shape) % 1000, *shape)
+    flow = fl if mode is not None else None
+    ref = co.level_forward(x1, x2, flow, 4, 1, 4, 1, 1, mode or 0, 0.1)
+    t1, t2, tf = to_dev(x1, x2, flow)
+    out = ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, mode or 0, 0.1, variant=variant)
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("shape", SHAPES[:5])
+@pytest.mark.parametrize("with_flow", [False, True])
+@pytest.mark.parametrize("slope", [None, 0.1])
+def test_backward_vs_oracle(shape, with_flow, slope):
+    x1, x2, fl = rand_case(7 + hash(shape) % 1000, *shape)
+    flow = fl if with_flow else None
+    fwd = co.level_forward(x1, x2, flow, 4, 1, 4, 1, 1, co.WARP_TORCH, slope)
+    g = np.random.RandomState(5).standard_normal(fwd.shape).astype(np.float32)
+    r1, r2, rf = co.level_backward(x1, x2, flow, g, 4, 1, 4, 1, 1, co.WARP_TORCH, slope)
+    t1, t2, tf, tg = to_dev(x1, x2, flow, g)
+    out = ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, slope)
+    g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, tg, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, slope)
+    assert rel_err(g1.cpu().numpy(), r1) < TOL
+    assert rel_err(g2.cpu().numpy(), r2) < TOL
+    if with_flow:
+        assert rel_err(gf.cpu().numpy(), rf) < TOL
+
+
+GENERIC = [(4, 1, 10, 1, 1), (3, 3, 4, 2, 2), (2, 1, 4, 1, 2), (6, 3, 4, 1, 1), (5, 1, 4, 2, 1), (8, 1, 8, 1, 1),
+           (0, 1, 2, 1, 1), (2, 1, 4, 1, 1), (6, 1, 4, 1, 1)]
+
+
+@pytest.mark.parametrize("p,k,md,s1,s2", GENERIC)
+@pytest.mark.parametrize("with_flow", [False, True])
+def test_general_parameters_vs_oracle(p, k, md, s1, s2, with_flow):
+    """pad != max_displacement (the reference's own __main__ case, correlation.py:87: pad 4,
+    md 10), kernel_size 3, both strides; forward and backward."""
+    x1, x2, fl = rand_case(11, 2, 12, 26, 28)
+    flow = fl if with_flow else None
+    ref = co.level_forward(x1, x2, flow, p, k, md, s1, s2, co.WARP_TORCH, 0.1)
+    t1, t2, tf = to_dev(x1, x2, flow)
+    out = ops.warp_corr_forward(t1, t2, tf, p, k, md, s1, s2, 1, cb.WARP_TORCH, 0.1)
+    assert tuple(out.shape) == ref.shape
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    g = np.random.RandomState(3).standard_normal(ref.shape).astype(np.float32)
+    r1, r2, rf = co.level_backward(x1, x2, flow, g, p, k, md, s1, s2, co.WARP_TORCH, 0.1)
+    g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, to_dev(g)[0], p, k, md, s1, s2, 1, cb.WARP_TORCH, 0.1)
+    assert rel_err(g1.cpu().numpy(), r1) < TOL
+    assert rel_err(g2.cpu().numpy(), r2) < TOL
+    if with_flow:
+        assert rel_err(gf.cpu().numpy(), rf) < TOL
+
+
+def test_flow_far_outside_every_border():
+    """Samples clipped at all four borders (stress set of SURVEY.md 8d: |flow| up to 3*md and
+    beyond): border clamp identical to ATen clip_coordinates, zero flow-gradient where clipped."""
+    x1, x2, fl = rand_case(21, 1, 16, 24, 40, sigma=15.0)
+    fl[:, :, :4] = 1e4
+    fl[:, :, -4:] = -1e4
+    ref = co.level_forward(x1, x2, fl, 4, 1, 4, 1, 1, co.WARP_TORCH, 0.1)
+    t1, t2, tf = to_dev(x1, x2, fl)
+    for v in (1, 3, 5):
+        assert rel_err(ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, variant=v).cpu().numpy(), ref) < TOL
+    g = np.random.RandomState(2).standard_normal(ref.shape).astype(np.float32)
+    out = ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1)
+    _, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, to_dev(g)[0], 4, 1, 4, 1, 1, 1, 0, 0.1)
+    _, r2, rf = co.level_backward(x1, x2, fl, g, 4, 1, 4, 1, 1, co.WARP_TORCH, 0.1)
+    assert rel_err(g2.cpu().numpy(), r2) < TOL and rel_err(gf.cpu().numpy(), rf) < TOL
+    assert torch.all(gf[:, :, :4] == 0) and torch.all(gf[:, :, -4:] == 0)
+
+
+# ------------------------------------------------------------------ dtypes, strides, surfaces
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("with_flow", [False, True])
+def test_half_precision_io(dtype, tol, with_flow):
+    """16-bit inputs/outputs, fp32 accumulation (the reference accumulates fp16 in fp16,
+    correlation_cuda_kernel.cu:40; bf16 is new)."""
+    x1, x2, fl = rand_case(31, 2, 40, 16, 40)
+    t1, t2, tf = to_dev(x1, x2, fl if with_flow else None)
+    h1, h2 = t1.to(dtype), t2.to(dtype)
+    ref = co.level_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), fl if with_flow else None, 4, 1, 4, 1, 1,
+                           co.WARP_TORCH, 0.1)
+    for v in (0, 3, 5):
+        out = ops.warp_corr_forward(h1, h2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, variant=v)
+        assert out.dtype == dtype
+        assert rel_err(out.float().cpu().numpy(), ref) < tol
+
+
+def test_output_into_concat_buffer_and_strided_inputs():
+    """write the activated cost volume straight into the decoder's
+    (B, 81+32+2, H, W) concat tensor; inputs that are channel slices of wider tensors."""
+    x1, x2, fl = rand_case(41, 2, 24, 16, 32)
+    ref = co.level_forward(x1, x2, fl, 4, 1, 4, 1, 1, co.WARP_TORCH, 0.1)
+    t1, t2, tf = to_dev(x1, x2, fl)
+    wide1 = torch.randn(2, 40, 16, 32, device=dev())
+    wide1[:, 8:32] = t1
+    cat = torch.full((2, 115, 16, 32), 7.0, device=dev())
+    for v in (1, 2, 3, 5):
+        cat.fill_(7.0)
+        ops.warp_corr_forward(wide1[:, 8:32], t2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, out=cat[:, :81], variant=v)
+        assert rel_err(cat[:, :81].cpu().numpy(), ref) < TOL
+        assert torch.all(cat[:, 81:] == 7.0)
+
+
+def test_reference_shaped_python_surfaces():
+    """Correlation (train -> autograd Function, eval -> raw op, correlation.py:72-80),
+    CorrelationFunction.apply, CorrelationTorch, torch.ops schemas."""
+    x1, x2, _ = rand_case(51, 2, 16, 12, 20)
+    ref = co.corr_forward(x1, x2, 4, 1, 4, 1, 1)
+    t1, t2 = to_dev(x1, x2)
+    m = cb.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    m.eval()
+    assert rel_err(m(t1, t2).cpu().numpy(), ref) < TOL
+    m.train()
+    a, b = t1.clone().requires_grad_(), t2.clone().requires_grad_()
+    y = m(a, b)
+    assert y.grad_fn is not None and rel_err(y.detach().cpu().numpy(), ref) < TOL
+    g = np.random.RandomState(9).standard_normal(ref.shape).astype(np.float32)
+    y.backward(to_dev(g)[0])
+    r1, r2 = co.corr_backward(x1, x2, g, 4, 1, 4, 1, 1)
+    assert rel_err(a.grad.cpu().numpy(), r1) < TOL and rel_err(b.grad.cpu().numpy(), r2) < TOL
+    assert rel_err(cb.CorrelationTorch(4)(t1, t2).cpu().numpy(), ref) < TOL
+    assert rel_err(torch.ops.cerberus_b200.correlation(t1, t2, 4, 1, 4, 1, 1, 1).cpu().numpy(), ref) < TOL
+    g1, g2 = torch.ops.cerberus_b200.correlation_backward(t1, t2, to_dev(g)[0], 4, 1, 4, 1, 1, 1)
+    assert rel_err(g1.cpu().numpy(), r1) < TOL and rel_err(g2.cpu().numpy(), r2) < TOL
+    cb.install(register_cerberus_ops=False)  # the cerberus:: alias is exercised in a subprocess below
+    from nnet_training.correlation_package.correlation import Correlation as RefPathCorrelation
+    assert RefPathCorrelation is cb.Correlation
+    # fused module: 2-argument form is the reference module, 3-argument form fuses warp + LeakyReLU
+    wm = cb.WarpCorrelation().eval()
+    assert rel_err(wm(t1, t2).cpu().numpy(), ref) < TOL
+
+
+def test_cerberus_namespace_alias_in_fresh_process():
+    """install() answers torch.ops.cerberus.correlation (schema of correlation_cuda.cpp:45-48) with our
+    kernels when the reference library is not loaded.  Own process: a torch library namespace can be
+    defined once, and test_reference_cuda_op.py loads the reference's own `cerberus` library."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); import cerberusnet_b200 as cb; cb.install();"
+        "x = torch.randn(1, 8, 12, 20, device='cuda');"
+        "a = torch.ops.cerberus.correlation(x, x, 4, 1, 4, 1, 1, 1);"
+        "b = cb.ops.warp_corr_forward(x, x, None, 4, 1, 4, 1, 1);"
+        "g1, g2 = torch.ops.cerberus.correlation_backward(x, x, torch.ones_like(a), 4, 1, 4, 1, 1, 1);"
+        "assert torch.equal(a, b) and g1.shape == x.shape; print('alias-ok')" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "alias-ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_decoder_call_site_pattern():
+    """The 3 reference ops of pwcnet_sfd.py:178-182 (flow_warp -> corr -> leaky_relu_) run
+    un-fused on our kernels give the same numbers as the fused launch."""
+    x1, x2, fl = rand_case(61, 1, 32, 16, 32)
+    t1, t2, tf = to_dev(x1, x2, fl)
+    corr = cb.Correlation(4, 1, 4, 1, 1, 1).eval()
+    unfused = corr(t1, cb.flow_warp(t2, tf).type(t1.dtype))
+    torch.nn.functional.leaky_relu(unfused, 0.1, inplace=True)
+    fused = cb.warp_correlation(t1, t2, tf)
+    assert rel_err(fused.cpu().numpy(), unfused.cpu().numpy()) < 1e-6
+    assert rel_err(fused.cpu().numpy(), co.level_forward(x1, x2, fl)) < TOL
+
+
+def test_trt_enqueue_adapter_and_host_call():
+    """The TensorRT-plugin-shaped entry (trt_plugins/correlation.hpp:31-32) and the host-buffer
+    entry give the same bytes as the device call."""
+    lib = cb.lib()
+    x1, x2, fl = rand_case(71, 2, 16, 16, 32)
+    t1, t2, tf = to_dev(x1, x2, fl)
+    ref = ops.warp_corr_forward(t1, t2, None, 4, 1, 4, 1, 1)
+    f = _lib.TrtCorrFields()
+    lib.cerb_trt_corr_default_fields(ctypes.byref(f))
+    descs = (_lib.TrtTensorDesc * 4)()
+    for i, dims in enumerate(((2, 16, 16, 32), (2, 16, 16, 32), (2, 2, 16, 32), (2, 81, 16, 32))):
+        descs[i].dims.nbDims = 4
+        for j, v in enumerate(dims):
+            descs[i].dims.d[j] = v
+    out = torch.zeros_like(ref)
+    ins = (ctypes.c_void_p * 3)(t1.data_ptr(), t2.data_ptr(), tf.data_ptr())
+    outs = (ctypes.c_void_p * 1)(out.data_ptr())
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert lib.cerb_trt_corr_enqueue(ctypes.byref(f), descs, ctypes.byref(descs[3]), ins, outs, None, stream) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # half precision descriptors (kHALF = 1)
+    for i in (0, 1, 3):
+        descs[i].type = 1
+    h1, h2 = t1.half(), t2.half()
+    outh = torch.zeros_like(ref, dtype=torch.float16)
+    ins = (ctypes.c_void_p * 3)(h1.data_ptr(), h2.data_ptr(), tf.data_ptr())
+    outs = (ctypes.c_void_p * 1)(outh.data_ptr())
+    assert lib.cerb_trt_corr_enqueue(ctypes.byref(f), descs, ctypes.byref(descs[3]), ins, outs, None, stream) == 0
+    torch.cuda.synchronize()
+    assert rel_err(outh.float().cpu().numpy(), co.corr_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), 4, 1, 4, 1, 1)) < 2e-3
+    # fused warp_correlation node, TensorRT warp convention
+    for i in (0, 1, 3):
+        descs[i].type = 0
+    ins = (ctypes.c_void_p * 3)(t1.data_ptr(), t2.data_ptr(), tf.data_ptr())
+    outs = (ctypes.c_void_p * 1)(out.data_ptr())
+    assert lib.cerb_trt_warp_corr_enqueue(ctypes.byref(f), 1, 0.1, descs, ctypes.byref(descs[3]), ins, outs, None, stream) == 0
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), co.level_forward(x1, x2, fl, 4, 1, 4, 1, 1, co.WARP_TRT, 0.1)) < TOL
+    # host buffers: H2D + kernel + D2H on the stream
+    p = _lib.make_params(t1, t2, tf, ref, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    need = lib.cerb_warp_corr_forward_host_workspace(ctypes.byref(p), 1)
+    ws = torch.empty(need, dtype=torch.uint8, device=dev())
+    h_out = torch.empty(ref.shape).pin_memory()
+    hx1, hx2, hfl = (torch.from_numpy(a).pin_memory() for a in (x1, x2, fl))
+    rc = lib.cerb_warp_corr_forward_host(ctypes.byref(p), _lib.ptr(hx1), _lib.ptr(hx2), _lib.ptr(hfl), _lib.ptr(h_out),
+                                         _lib.ptr(ws), need, stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert rel_err(h_out.numpy(), co.level_forward(x1, x2, fl)) < TOL
+    assert lib.cerb_warp_corr_forward_host(ctypes.byref(p), _lib.ptr(hx1), _lib.ptr(hx2), _lib.ptr(hfl),
+                                           _lib.ptr(h_out), _lib.ptr(ws), 16, stream) == -5
+
+
+def test_cuda_graph_capture_and_stream_respect():
+    """No allocation, no host sync, launches only on the caller's stream: the call is
+    graph-capturable (the reference plugin's three host syncs are not)."""
+    x1, x2, fl = rand_case(81, 1, 32, 32, 64)
+    t1, t2, tf = to_dev(x1, x2, fl)
+    out = torch.zeros(1, 81, 32, 64, device=dev())
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, out=out)
+        torch.cuda.synchronize()
+        out.zero_()
+        with torch.cuda.graph(g, stream=s):
+            ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, out=out)
+    assert float(out.abs().max()) == 0.0  # capture does not execute
+    g.replay()
+    torch.cuda.synchronize()
+    assert rel_err(out.cpu().numpy(), co.level_forward(x1, x2, fl)) < TOL
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_config2_finest_level():
+    """BASELINE.json configs[1] finest level (C=32, 128x256): too big for the scalar oracle in a
+    unit test, so size-independent properties: (a) variants agree, (b) linearity in x1,
+    (c) displacement symmetry corr(a,b)[d](p) == corr(b,a)[-d](p+d), (d) channel-mean identity at
+    zero displacement, (e) a random sample of outputs against a float64 dot product."""
+    torch.manual_seed(0)
+    a = torch.randn(1, 32, 128, 256, device=dev())
+    b = torch.randn(1, 32, 128, 256, device=dev())
+    c = torch.randn(1, 32, 128, 256, device=dev())
+    ab = ops.warp_corr_forward(a, b, None, 4, 1, 4, 1, 1, variant=1)
+    for v in (2, 3, 5):
+        assert rel_err(ops.warp_corr_forward(a, b, None, 4, 1, 4, 1, 1, variant=v).cpu().numpy(), ab.cpu().numpy()) < 2e-6
+    lin = ops.warp_corr_forward(2.0 * a + c, b, None, 4, 1, 4, 1, 1)
+    cb_ = ops.warp_corr_forward(c, b, None, 4, 1, 4, 1, 1)
+    assert rel_err(lin.cpu().numpy(), (2.0 * ab + cb_).cpu().numpy()) < 5e-6
+    ba = ops.warp_corr_forward(b, a, None, 4, 1, 4, 1, 1)
+    for (dy, dx) in [(0, 0), (1, -2), (-4, 4), (3, 3)]:
+        d, dm = (dy + 4) * 9 + (dx + 4), (-dy + 4) * 9 + (-dx + 4)
+        ys, xs = slice(max(0, -dy), 128 - max(0, dy)), slice(max(0, -dx), 256 - max(0, dx))
+        ys2, xs2 = slice(max(0, dy), 128 - max(0, -dy)), slice(max(0, dx), 256 - max(0, -dx))
+        assert rel_err(ab[0, d, ys, xs].cpu().numpy(), ba[0, dm, ys2, xs2].cpu().numpy()) < 2e-6
+    assert rel_err(ab[0, 40].cpu().numpy(), (a * b).mean(1)[0].cpu().numpy()) < 2e-6
+    rs = np.random.RandomState(0)
+    an, bn, abn = a.cpu().double().numpy(), b.cpu().double().numpy(), ab.cpu().numpy()
+    for _ in range(200):
+        y, x, dy, dx = rs.randint(128), rs.randint(256), rs.randint(-4, 5), rs.randint(-4, 5)
+        yy, xx = y + dy, x + dx
+        want = 0.0 if not (0 <= yy < 128 and 0 <= xx < 256) else float((an[0, :, y, x] * bn[0, :, yy, xx]).mean())
+        assert abs(abn[0, (dy + 4) * 9 + dx + 4, y, x] - want) < 1e-5 * np.abs(abn).max()
+
+
+def test_full_size_fused_against_stock_composition():
+    """Whole PWC pyramid of configs[1] against the stock composition on the same GPU: ATen
+    grid_sample (the reference's flow_warp arithmetic, UnFlowLoss.py:83-94) -> our plain
+    correlation -> leaky_relu.  Ties the fused warp to the real ATen CUDA kernel at full size."""
+    from oracle import torch_oracle as to
+    torch.manual_seed(1)
+    for (C, H, W) in [(128, 16, 32), (96, 32, 64), (64, 64, 128), (32, 128, 256)]:
+        x1 = torch.randn(1, C, H, W, device=dev())
+        x2 = torch.randn(1, C, H, W, device=dev())
+        fl = (torch.randn(1, 2, H, W, device=dev()) * 1.5).clamp(-6, 6)
+        warped = to.flow_warp(x2, fl, to.WARP_TORCH)
+        stock = torch.nn.functional.leaky_relu(ops.warp_corr_forward(x1, warped, None, 4, 1, 4, 1, 1), 0.1)
+        fused = cb.warp_correlation(x1, x2, fl)
+        assert rel_err(fused.cpu().numpy(), stock.cpu().numpy()) < TOL
+        assert rel_err(cb.flow_warp(x2, fl).cpu().numpy(), warped.cpu().numpy()) < 2e-6
+
+
+def test_launch_counter_moves():
+    n0 = cb.lib().cerb_launch_count()
+    x = torch.randn(1, 8, 16, 32, device=dev())
+    ops.warp_corr_forward(x, x, None, 4, 1, 4, 1, 1)
+    assert cb.lib().cerb_launch_count() == n0 + 1
