@@ -39,6 +39,10 @@ MD, PAD, D2 = 4, 4, 81
 SLOPE = 0.1
 N_SETS = 10  # 10 x 29.3 MB of inputs+outputs = 293 MB > 2 x 126 MB L2
 FMA_PEAK_TFLOPS = 70.4  # measured on this pool with tools/microbench/pipes.cu (FFMA2, sustained)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the finest-level kernel, from the
+# ncu --set full capture summarised in profiles/r01_ncu_fwd_finest_level.txt (reads = algorithmic
+# input bytes; the 10.6 MB of output is still dirty in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES_FINEST = 8723200
 
 
 def level_bytes(C, H, W, warped, B=1, e=4):
@@ -290,8 +294,8 @@ def main_gpu(args, rank, world, local_rank):
     t_fma = level_flops(dom["C"], dom["H"], dom["W"]) / (FMA_PEAK_TFLOPS * 1e12)
     roofline = {
         "bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
-        "traffic": None, "peak_source": peak_src,
-        "kernel": f"warp_corr_fwd_kernel<float,8,32,1> level {dom['level']} (C={dom['C']}, {dom['H']}x{dom['W']})",
+        "traffic": NCU_TRAFFIC_BYTES_FINEST, "traffic_source": "profiles/r01_ncu_fwd_finest_level.txt", "peak_source": peak_src,
+        "kernel": f"warp_corr_fwd_kernel<float,8,32,1,4,3> level {dom['level']} (C={dom['C']}, {dom['H']}x{dom['W']})",
         "algorithmic_bytes_per_launch": int(dom["algorithmic_MB"] * 1e6),
         "avg_launch_us": dom["us_per_launch"],
         "binding_roof_frac": round(max(t_hbm, t_fma) * 1e6 / dom["us_per_launch"], 4),
