@@ -75,7 +75,7 @@ struct FwdCfg {
   static constexpr size_t SMEM_OUT = (SMEM_RAW + sizeof(float) * RS * RAW_STAGE + 1023) / 1024 * 1024;
   static constexpr size_t SMEM_RED = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
   static constexpr size_t SMEM_BAR = SMEM_RED + sizeof(int) * 2 * kProducerWarps * 4;  // (kGatherWarps rows used)
-  static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * kStages + 2 * RS) * sizeof(uint64_t) + 1024;
+  static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * kStages + 2 * RS + 2) * sizeof(uint64_t) + 1024;
   static_assert(NCONS % 32 == 0, "consumer threads must be whole warps");
   static_assert((sizeof(float) * X1_STAGE) % 1024 == 0, "x1 stage must keep 1024-byte alignment");
   static_assert((sizeof(float) * X2_STAGE) % 128 == 0 && (sizeof(float) * RAW_STAGE) % 128 == 0, "TMA dst alignment");
@@ -128,6 +128,8 @@ struct FwdArgs {
   int use_tma_x2;   // un-warped x2 halo tiles by TMA (flow == null)
   int use_tma_raw;  // raw x2 source boxes by TMA, warp gathered from shared memory
   int use_tma_out;  // output tile by TMA store
+  int csplit_log2;
+  int csplit;       // CTAs per cluster sharing one tile, each taking a slice of the channel chunks (1 = off)
   long long* dbg;   // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 64 slots per CTA
 };
 
@@ -137,6 +139,14 @@ template <int TX>
 __device__ __forceinline__ int swz_chunk(int row, int chunk) {
   if constexpr (TX == 32) return chunk ^ (row & 7);
   else return chunk;
+}
+// 16-wide tiles have no TMA swizzle; when the tile is not going through TMA (cluster split) the
+// 4 chunks of a row are XOR-ed with two more row bits so the accumulator stores of one warp spread
+// over the banks (8-way conflicts otherwise).  Involution: the same function maps back.
+template <int TX>
+__device__ __forceinline__ int swz_partial(int row, int chunk, bool on) {
+  if constexpr (TX == 16) return on ? (chunk ^ ((row >> 1) & 3)) : chunk;
+  else return swz_chunk<TX>(row, chunk);
 }
 
 // ------------------------------------------------------------------ fast kernel ----------
@@ -158,6 +168,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* raw_full = empty_bar + kStages;
   uint64_t* raw_empty = raw_full + RS;
+  uint64_t* part_bar = raw_empty + RS;  // cluster split: every CTA's partial tile is in its shared memory
+  uint64_t* done_bar = part_bar + 1;     // cluster split: every CTA has finished reading the partial tiles
 
   const Geom& g = a.g;
   const int tid = threadIdx.x;
@@ -173,6 +185,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], kGatherWarps);
     }
+    mbar_init(part_bar, (uint32_t)a.csplit);
+    mbar_init(done_bar, (uint32_t)a.csplit);
     fence_barrier_init();
     if (a.use_tma_in) tma_prefetch_desc(&tm_x1);
     if (a.use_tma_x2) tma_prefetch_desc(&tm_x2);
@@ -180,6 +194,14 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     if (a.use_tma_out) tma_prefetch_desc(&tm_out);
   }
   __syncthreads();
+  // cluster channel split: CTA `crank` of a cluster of `csplit` CTAs handles chunks [ck_begin, ck_end)
+  // of the cluster's tile; remote mbarriers must be initialised before anyone signals them
+  // (csplit is a power of two: shifts, not divisions -- this runs on every thread's critical path)
+  const int S = a.csplit, Slog = a.csplit_log2;
+  const int crank = S > 1 ? (int)cluster_ctarank() : 0;
+  if (S > 1) cluster_sync_all();
+  const int tile0 = (int)blockIdx.x >> Slog, tile_step = (int)gridDim.x >> Slog;
+  const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
   if (tid == 0) CERB_TRACE(0);
 
   int stage = 0;
@@ -201,7 +223,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       // ---------------------------- TMA warp ----------------------------
       int ri = 0, xs = 0;
       uint32_t riphase = 0, xphase = 0;
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
         const int n = tile / (a.tiles_x * a.tiles_y);
         const int trem = tile - n * (a.tiles_x * a.tiles_y);
         const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
@@ -212,10 +234,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         // are still computing sample positions and the bounding box
         int x1_pre = 0;
         if (reduce_bbox && a.use_tma_in && lane == 0) {
-          for (; x1_pre < kStages && x1_pre < a.nchunks; ++x1_pre) {
+          for (; x1_pre < kStages && ck_begin + x1_pre < ck_end; ++x1_pre) {
             mbar_wait(&empty_bar[xs], xphase ^ 1);
             mbar_arrive_expect_tx(&full_bar[xs], (uint32_t)(sizeof(float) * Cfg::X1_STAGE));
-            tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, x1_pre * CC, n);
+            tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, (ck_begin + x1_pre) * CC, n);
             if (++xs == kStages) { xs = 0; xphase ^= 1; }
           }
         }
@@ -234,14 +256,14 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           if (xmin <= xmax && xmax - ox < Cfg::RAW_W && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
         }
         if (lane == 0) {
-          for (int ck = 0; ck < a.nchunks; ++ck) {
+          for (int ck = ck_begin; ck < ck_end; ++ck) {
             if (path == PATH_RAW) {
               mbar_wait(&raw_empty[ri], riphase ^ 1);
               mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
               tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
               if (++ri == RS) { ri = 0; riphase ^= 1; }
             }
-            if (ck < x1_pre) continue;  // x1 tile already requested above
+            if (ck - ck_begin < x1_pre) continue;  // x1 tile already requested above
             mbar_wait(&empty_bar[xs], xphase ^ 1);
             const uint32_t tx = (a.use_tma_in ? (uint32_t)(sizeof(float) * Cfg::X1_STAGE) : 0u) +
                                 (path == PATH_TMA_X2 ? (uint32_t)(sizeof(float) * Cfg::X2_STAGE) : 0u);
@@ -292,7 +314,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       };
 
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
         const int n = tile / (a.tiles_x * a.tiles_y);
         const int trem = tile - n * (a.tiles_x * a.tiles_y);
         const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
@@ -302,7 +324,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
         // ------------- un-warped second map: the TMA warp loads the halo tile as a box -------------
         if (!warped && a.use_tma_x2) {
-          for (int ck = 0; ck < a.nchunks; ++ck) {
+          for (int ck = ck_begin; ck < ck_end; ++ck) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
             publish_stage();
@@ -383,7 +405,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
         if (path == PATH_RAW) {
           // ------------- warp gathered from the raw source box in shared memory -------------
-          for (int ck = 0; ck < a.nchunks; ++ck) {
+          for (int ck = ck_begin; ck < ck_end; ++ck) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
             if (gt == 0 && ck < 4) CERB_TRACE(44 + 3 * ck);
@@ -424,7 +446,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         constexpr int NB = CC / kCBatch;
         constexpr int NV = Cfg::POS_PER_THREAD * kCBatch * 4;
         const T* x2n = x2 + (long long)n * g.x2s[0];
-        const int total_batches = a.nchunks * NB;
+        const int total_batches = (ck_end - ck_begin) * NB;
+        const int gb0 = ck_begin * NB;
         float cur[NV], nxt[NV];
         auto issue = [&](int gb, float (&dst)[NV]) {
           const int chb = gb * kCBatch;
@@ -446,10 +469,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             }
           }
         };
-        issue(0, cur);
+        if (total_batches > 0) issue(gb0, cur);
         for (int gb = 0; gb < total_batches; ++gb) {
-          if (gb + 1 < total_batches) issue(gb + 1, nxt);
-          const int ck = gb / NB, bi = gb - ck * NB;
+          if (gb + 1 < total_batches) issue(gb0 + gb + 1, nxt);
+          const int ck = (gb0 + gb) / NB, bi = (gb0 + gb) - ck * NB;
           float* x2dst = x2s + stage * Cfg::X2_STAGE;
           if (bi == 0) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -487,8 +510,9 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
     for (int h = 0; h < 2; ++h) x1_off[h] = y * TX + swz_chunk<TX>(y, strip * 2 + h) * 4;  // row = c*TY + y; TY % 8 == 0 or TX < 32
 
+    int tiles_done = 0;
     if (tid == 0) CERB_TRACE(16);
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
       const int n = tile / (a.tiles_x * a.tiles_y);
       const int trem = tile - n * (a.tiles_x * a.tiles_y);
       const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
@@ -497,7 +521,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
       for (int i = 0; i < 8 * kD; ++i) acc[i] = 0.f;
 
-      for (int ck = 0; ck < a.nchunks; ++ck) {
+      for (int ck = ck_begin; ck < ck_end; ++ck) {
         mbar_wait(&full_bar[stage], phase);
         if (tid == 0 && ck < 8) CERB_TRACE(17 + 2 * ck);
         const float* x1p = x1s + stage * Cfg::X1_STAGE;
@@ -531,10 +555,15 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       if (tid == 0) CERB_TRACE(40);
 
       // ---------------- epilogue: /C, LeakyReLU, stage tile, TMA store ----------------
-      if (a.use_tma_out) {
+      const bool finalize_local = (KS == 1) || (S == 1);  // the cluster split is only used with KS > 1
+      if (S > 1) {
+        // our partial buffer may still be read by cluster mates (previous tile)
+        if (tiles_done > 0) mbar_wait_cluster(done_bar, (uint32_t)((tiles_done - 1) & 1));
+      } else if (a.use_tma_out) {
         if (tid == 0) tma_store_wait_read0();  // previous tile's store has finished reading `outs`
       }
       named_bar_sync(1, Cfg::NCONS);
+      if (tid == 0) CERB_TRACE(35);
       float* obuf = outs + grp * Cfg::OUT_TILE;
 #pragma unroll
       for (int dx = 0; dx < kD; ++dx) {
@@ -547,26 +576,87 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           for (int e = 0; e < 4; ++e) {
             float r = acc[(4 * h + e) * kD + dx];
             if constexpr (KS == 1) {
-              r = div_const(r, divisor, rdivisor);
-              if (g.has_act) r = leaky(r, g.slope);
+              if (finalize_local) {
+                r = div_const(r, divisor, rdivisor);
+                if (g.has_act) r = leaky(r, g.slope);
+              }
             }
             vv[e] = r;
           }
-          *reinterpret_cast<float4*>(obuf + row * TX + swz_chunk<TX>(row, strip * 2 + h) * 4) = v;
+          *reinterpret_cast<float4*>(obuf + row * TX + swz_partial<TX>(row, strip * 2 + h, S > 1) * 4) = v;
         }
       }
+      if (tid == 0) CERB_TRACE(36);
       if constexpr (KS > 1) {
         named_bar_sync(1, Cfg::NCONS);
+        if (tid == 0) CERB_TRACE(37);
         for (int e = tid; e < Cfg::OUT_TILE; e += Cfg::NCONS) {
           float s = outs[e];
 #pragma unroll
           for (int k2 = 1; k2 < KS; ++k2) s += outs[k2 * Cfg::OUT_TILE + e];
-          s = div_const(s, divisor, rdivisor);
-          if (g.has_act) s = leaky(s, g.slope);
+          if (finalize_local) {
+            s = div_const(s, divisor, rdivisor);
+            if (g.has_act) s = leaky(s, g.slope);
+          }
           outs[e] = s;
         }
       }
-      if (a.use_tma_out) {
+      if constexpr (KS > 1) if (S > 1) {
+        // ---- cluster reduction of the S partial tiles through distributed shared memory ----
+        if (tid == 0) CERB_TRACE(38);
+        named_bar_sync(1, Cfg::NCONS);            // this CTA's partial tile is complete
+        if (tid < S) {  // one thread per cluster rank: a single cluster-scope fence, then a relaxed arrive each
+          fence_acq_rel_cluster();
+          mbar_arrive_remote_relaxed(mapa_u32(smem_u32(part_bar), (uint32_t)tid));
+        }
+        if (tid == 0) CERB_TRACE(39);
+        mbar_wait_cluster(part_bar, (uint32_t)(tiles_done & 1));
+        const int slice = Cfg::OUT_TILE / S;      // host guarantees divisibility
+        const uint32_t obase = smem_u32(outs);
+        T* outp = (T*)a.out + (long long)n * g.os[0];
+        if (tid == 0) CERB_TRACE(43);
+        // 16-byte remote loads, all issued before the first sum (DSMEM latency ~200 cycles)
+        const int units = slice / 4;                    // float4 units of this CTA's slice
+        constexpr int kUPT = (Cfg::OUT_TILE / 8 + Cfg::NCONS - 1) / Cfg::NCONS;  // S >= 2
+        float4 pv[kUPT][8];
+#pragma unroll
+        for (int i = 0; i < kUPT; ++i) {
+          const int u = tid + i * Cfg::NCONS;
+          const uint32_t addr = obase + 16u * (uint32_t)(crank * units + u);
+#pragma unroll
+          for (int r = 0; r < 8; ++r)
+            pv[i][r] = (r < S && u < units) ? ld_dsmem_v4(mapa_u32(addr, (uint32_t)r)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < kUPT; ++i) {
+          const int u = tid + i * Cfg::NCONS;
+          if (u < units) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { s4.x += pv[i][r].x; s4.y += pv[i][r].y; s4.z += pv[i][r].z; s4.w += pv[i][r].w; }
+            const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+            // physical chunk -> logical position of the [plane][y][x] tile (undo the partial-tile swizzle)
+            const int pchunk = crank * units + u;
+            const int row = pchunk / (TX / 4), lchunk = swz_partial<TX>(row, pchunk - row * (TX / 4), true);
+            const int plane = row / TY, yy = row - plane * TY;
+            const int oy = by0 + yy;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float s = div_const(sv[k], divisor, rdivisor);
+              if (g.has_act) s = leaky(s, g.slope);
+              const int ox = bx0 + lchunk * 4 + k;
+              if (oy < g.outH && ox < g.outW)
+                outp[(long long)plane * g.os[1] + (long long)oy * g.os[2] + ox] = from_f32<T>(s);
+            }
+          }
+        }
+        if (tid == 0) CERB_TRACE(41);
+        named_bar_sync(1, Cfg::NCONS);            // all of this CTA's remote reads are done
+        if (tid < S) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(done_bar), (uint32_t)tid));
+      }
+      if (S > 1) {
+        // output already written by the cluster reduction above
+      } else if (a.use_tma_out) {
         fence_proxy_async_smem();
         named_bar_sync(1, Cfg::NCONS);
         if (tid == 0) {
@@ -588,10 +678,11 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         }
         named_bar_sync(1, Cfg::NCONS);  // `outs` is rewritten by the next tile's epilogue
       }
+      ++tiles_done;
     }
-    // the tile buffer only has to outlive the store's shared-memory reads; the writes are
-    // complete at kernel end like any other store
-    if (a.use_tma_out && tid == 0) tma_store_wait_read0();
+    // cluster mates may still be reading this CTA's partial tile: do not exit before they are done
+    if (S > 1 && tiles_done > 0) mbar_wait_cluster(done_bar, (uint32_t)((tiles_done - 1) & 1));
+    if (S == 1 && a.use_tma_out && tid == 0) tma_store_wait_read0();
     if (tid == 0) CERB_TRACE(42);
   }
 }
@@ -697,7 +788,7 @@ static int num_sms() {
 
 template <typename T, int TY, int TX, int KS, int CC, int RS>
 static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
-                               int force_no_tma, cudaStream_t stream) {
+                               int force_no_tma, bool allow_csplit, cudaStream_t stream) {
   using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
   FwdArgs a;
   a.g = g;
@@ -736,8 +827,38 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int grid = a.total_tiles < num_sms() ? a.total_tiles : num_sms();
-  kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(a, tm_x1, tm_x2, tm_raw, tm_out);
+  // coarse pyramid levels have fewer tiles than SMs: split the channel chunks of each tile over a
+  // thread-block cluster (partial tiles reduced through DSMEM in the epilogue)
+  int S = 1;
+  if (allow_csplit && TX < 32 && !getenv("CERB_DEBUG_NO_CSPLIT")) {
+    while (S < 8 && a.total_tiles * (S * 2) <= num_sms() && a.nchunks >= S * 2 && (Cfg::OUT_TILE % (S * 2 * 4)) == 0) S *= 2;
+  }
+  a.csplit = S;
+  a.csplit_log2 = S == 8 ? 3 : S == 4 ? 2 : S == 2 ? 1 : 0;
+  if (S > 1) a.use_tma_out = 0;
+  int nclusters = num_sms() / S;
+  if (nclusters > a.total_tiles) nclusters = a.total_tiles;
+  const int grid = nclusters * S;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(Cfg::NTHREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (S > 1) {
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_x1, tm_x2, tm_raw, tm_out);
+    if (le != cudaSuccess) return le;
+  } else {
+    // no cluster attribute for the plain launch: a 1-CTA "cluster" still switches the CTA scheduler
+    // and costs ~2 us on a one-wave grid
+    kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(a, tm_x1, tm_x2, tm_raw, tm_out);
+  }
   return cudaGetLastError();
 }
 
@@ -753,8 +874,8 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
       const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8);
       small = big_tiles < (long long)num_sms() * 3 / 4;
     }
-    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, stream);
-    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, stream);
+    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, true, stream);
+    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, false, stream);
   }
   const long long total = (long long)g.B * g.D2 * g.outH * g.outW;
   long long blocks = (total + 255) / 256;
