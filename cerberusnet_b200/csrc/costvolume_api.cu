@@ -251,6 +251,7 @@ int cerb_warp_corr_forward_host(const cerb_corr_params* p, const void* h_x1, con
 
 // Debugging aid, not part of the public ABI: per-CTA clock64() trace of the fast forward kernel.
 CERB_API void cerb_debug_set_trace_buffer(void* dev_ptr) { cerb::set_trace_buffer((long long*)dev_ptr); }
+CERB_API void cerb_debug_set_trace_iter(int it) { cerb::set_trace_iter(it); }
 
 uint64_t cerb_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 

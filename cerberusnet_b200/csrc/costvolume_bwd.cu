@@ -9,18 +9,14 @@
 // All batch items in one launch (the reference launches 2*B kernels, .cu:386,407), no padded NHWC
 // scratch, no memsets except grad_x2 when it is splatted through the warp.
 //
-// Fast path (k=1, s1=s2=1, md=4).  Both gradients are the same banded contraction
-//     g[c, p] = 1/C * sum_d  G[d, p] * S[c, p (+/-) d]
-// so one kernel template serves both: a 256-thread CTA owns an 8x32 pixel tile, every thread
-// keeps its pixel's 81 cost-volume gradients (LeakyReLU mask applied) in registers and walks the
-// channels, reading the 9x9 window of S from a shared-memory halo tile that is staged per
-// 8-channel chunk (for grad_x1 that tile is the *re-warped* x2, gathered on the fly).
-// For grad_x2 the per-channel result is pushed straight through the bilinear warp backward:
-// 4 atomics into grad_x2 and the flow gradient accumulated over channels in registers.
+// Fast path (k=1, s1=s2=1, md=4): corr_bwd_tiled_kernel below, one template for both gradients.
 #include "costvolume_common.cuh"
 #include "costvolume_launch.h"
 
 namespace cerb {
+
+long long* get_trace_buffer();
+#define BWD_TRACE(slot) do { if (a.dbg && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && threadIdx.x == 0) a.dbg[(slot)] = clock64(); } while (0)
 
 constexpr int kMDb = 4;
 constexpr int kDb = 9;
@@ -38,6 +34,7 @@ template <> __device__ __forceinline__ void atomic_add_t<__nv_bfloat16>(__nv_bfl
 }
 
 struct BwdArgs {
+  long long* dbg;  // optional clock64 trace of CTA 0 (cerb_debug_set_trace_buffer)
   Geom g;
   const void* x1;
   const void* x2;
@@ -51,60 +48,98 @@ struct BwdArgs {
   int tiles_x, tiles_y;
 };
 
-// WHICH == 0: grad_x1 (S = warped x2, window p + d).  WHICH == 1: grad_x2 (S = x1, window q - d).
+// Register-tiled backward.  Both gradients have the form
+//     g[c, q] = 1/C * sum_e  G[e, q] * S[c, q + e],      e in [-4,4]^2
+//   WHICH 0 (grad_x1):  G[e, q] = gO'[e, q]            S = warped x2      (q = x1 pixel)
+//   WHICH 1 (grad_x2w): G[e, q] = gO'[-e, q + e]       S = x1             (q = warped-map pixel)
+// with gO' = grad_out masked by the LeakyReLU of the saved output.  One CTA per 8x32 tile of q:
+//   * the whole G tile (81 planes x 8 x 32, 83 KB) is built once and stays in shared memory;
+//   * 32 channels of the S halo tile (16 x 40, re-warped on the fly for grad_x1) per chunk;
+//   * thread = (8-pixel strip, row, 4 channels): 32 accumulators, per row displacement the 9 x 8
+//     slice of G in registers (LDS.128 broadcast across the 8 channel-subset lanes) and, per
+//     channel, one 16-float row of S (4 LDS.128) -> 72 FFMA;
+//   * results are staged through shared memory and written coalesced; for grad_x2 with a flow
+//     they go straight through the bilinear-warp backward (4 atomics, flow gradient in registers).
+constexpr int BS_XS = 44;                      // S row stride (floats)
+constexpr int BS_CH = BH_Y * BS_XS + 4;        // S channel stride: == 4 (mod 32) -> 8 channels hit 8 bank groups
+constexpr int BCH = 32;                        // channels per chunk
+constexpr int BO_CH = BT_Y * BT_X + 4;         // staged-output channel stride
+constexpr int BG_FLOATS = kD2b * BT_Y * BT_X;  // 20736
+constexpr size_t BWD_SMEM = sizeof(float) * (BG_FLOATS + BCH * BS_CH);
+
 template <typename T, int WHICH>
-__global__ void __launch_bounds__(256) corr_bwd_fast_kernel(const BwdArgs a) {
-  __shared__ float halo[kCB * BH_Y * BH_XS];
+__global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) float bsm[];
+  float* Gs = bsm;                  // [81][8][32]
+  float* Ss = bsm + BG_FLOATS;      // [32][BS_CH]   (aliased by the staged output [32][BO_CH])
   const Geom& g = a.g;
   const int tid = threadIdx.x;
-  const int ty = tid >> 5, tx = tid & 31;
   const int n = blockIdx.z;
-  const int iy0 = blockIdx.y * BT_Y, ix0 = blockIdx.x * BT_X;  // input-frame tile origin
-  const int iy = iy0 + ty, ix = ix0 + tx;
-  const bool pix_ok = iy < g.H && ix < g.W;
+  const int iy0 = blockIdx.y * BT_Y, ix0 = blockIdx.x * BT_X;
   const T* __restrict__ x1 = (const T*)a.x1 + (long long)n * g.x1s[0];
   const T* __restrict__ x2 = (const T*)a.x2 + (long long)n * g.x2s[0];
   const T* __restrict__ gout = (const T*)a.gout + (long long)n * g.os[0];
   const T* __restrict__ outp = a.out ? (const T*)a.out + (long long)n * g.os[0] : nullptr;
   const bool warped = a.flow != nullptr;
+  const bool mask = g.has_act && outp != nullptr;
 
-  // ---- the pixel's 81 cost-volume gradients, activation mask applied
-  float G[kD2b];
+  BWD_TRACE(WHICH * 32 + 0);
+  // ---- G tile: thread = pixel of the tile, planes in batches of 9 (18 independent loads in flight)
+  {
+    const int ty = tid >> 5, tx = tid & 31;
+    const int qy = iy0 + ty, qx = ix0 + tx;
+    const bool q_ok = qy < g.H && qx < g.W;
+#pragma unroll 1
+    for (int dy0 = 0; dy0 < kDb; dy0 += 3) {
+      // Loads are unconditional from clamped (always valid) addresses and validity is applied
+      // afterwards: with only 7 predicate registers the compiler otherwise consumes each predicated
+      // load right after issuing it and the 54 loads serialise.
+      float gvv[3 * kDb], ovv[3 * kDb];
 #pragma unroll
-  for (int dy = 0; dy < kDb; ++dy) {
-#pragma unroll
-    for (int dx = 0; dx < kDb; ++dx) {
-      // WHICH 0: output pixel of this input pixel.  WHICH 1: output pixel of source p = q - d.
-      const int py = (WHICH == 0) ? iy : iy - (dy - kMDb);
-      const int px = (WHICH == 0) ? ix : ix - (dx - kMDb);
-      const int oy = py - a.off, ox = px - a.off;
-      float v = 0.f;
-      if (pix_ok && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW) {
-        const long long o = (long long)(dy * kDb + dx) * g.os[1] + (long long)oy * g.os[2] + ox;
-        v = ldg_f32(gout + o);
-        if (g.has_act && outp != nullptr && !(ldg_f32(outp + o) > 0.f)) v *= g.slope;
+      for (int r = 0; r < 3 * kDb; ++r) {
+        const int dyi = dy0 + r / kDb, dxi = r % kDb;
+        const int plane = dyi * kDb + dxi;
+        const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
+        const int d = (WHICH == 0) ? plane : (kD2b - 1 - plane);
+        const int oy = min(max(py - a.off, 0), g.outH - 1), ox = min(max(px - a.off, 0), g.outW - 1);
+        const long long o = (long long)d * g.os[1] + (long long)oy * g.os[2] + ox;
+        gvv[r] = ldcg_f32(gout + o);
+        ovv[r] = mask ? ldcg_f32(outp + o) : 1.f;
       }
-      G[dy * kDb + dx] = v;
+#pragma unroll
+      for (int r = 0; r < 3 * kDb; ++r) {
+        const int dyi = dy0 + r / kDb, dxi = r % kDb;
+        const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
+        const int oy = py - a.off, ox = px - a.off;
+        const bool ok = q_ok && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
+        float v = ok ? gvv[r] : 0.f;
+        if (!(ovv[r] > 0.f)) v *= g.slope;   // ovv == 1 when there is no activation
+        Gs[(dy0 * kDb + r) * (BT_Y * BT_X) + tid] = v;
+      }
+      BWD_TRACE(WHICH * 32 + 6 + dy0 / 3);
     }
   }
 
-  // ---- staging plan: halo positions handled by this thread
+  // ---- staging plan for the S halo tile: positions handled by this thread (fixed for the tile)
   constexpr int NPOS = BH_Y * BH_X;
   constexpr int PPT = (NPOS + 255) / 256;
   Taps taps[PPT];
   int sdst[PPT];
   unsigned valid_mask = 0;
+  const bool gather = (WHICH == 0) && warped;
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int i = tid + j * 256;
     sdst[j] = -1;
+    taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = 0;
+    taps[j].w[0] = taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
     if (i < NPOS) {
       const int hy = i / BH_X, hx = i - hy * BH_X;
-      sdst[j] = hy * BH_XS + hx;
+      sdst[j] = hy * BS_XS + hx;
       const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + hx;
       if (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) {
         valid_mask |= 1u << j;
-        if (WHICH == 0 && warped) {
+        if (gather) {
           const float* fp = a.flow + (long long)n * g.fls[0] + (long long)qy * g.fls[2] + qx;
           bool in_x, in_y;
           const float sx = sample_pos(qx, __ldg(fp), g.W, g.warp_mode, in_x);
@@ -112,100 +147,185 @@ __global__ void __launch_bounds__(256) corr_bwd_fast_kernel(const BwdArgs a) {
           taps[j] = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
         } else {
           const long long hs = (WHICH == 0) ? g.x2s[2] : g.x1s[2];
-          const int o = (int)(qy * hs) + qx;
-          taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = o;
-          taps[j].w[0] = 1.f; taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
+          taps[j].off[0] = (int)(qy * hs) + qx;
+          taps[j].w[0] = 1.f;
         }
       }
     }
   }
 
-  // ---- WHICH 1 + warp: this pixel's own bilinear taps for the splat and the flow gradient
+  // ---- roles
+  const int subset = tid & 7, combo = tid >> 3;   // compute: 8 channel subsets x 32 (strip,row) combos
+  const int strip = combo & 3, yrow = combo >> 2;
+  const int wty = tid >> 5, wtx = tid & 31;       // write-out: one pixel per thread
+  const int wy = iy0 + wty, wx = ix0 + wtx;
+  const bool wpix_ok = wy < g.H && wx < g.W;
+
+  // grad_x2 with a flow: this pixel's bilinear taps for the splat and the flow gradient
   Taps mytap;
   bool in_x = false, in_y = false;
-  float gix = 0.f, giy = 0.f;
-  float wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;
-  if (WHICH == 1 && warped && pix_ok) {
-    const float* fp = a.flow + (long long)n * g.fls[0] + (long long)iy * g.fls[2] + ix;
-    const float sx = sample_pos(ix, __ldg(fp), g.W, g.warp_mode, in_x);
-    const float sy = sample_pos(iy, __ldg(fp + g.fls[1]), g.H, g.warp_mode, in_y);
+  float gix = 0.f, giy = 0.f, wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;
+  int sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0;
+  if (WHICH == 1 && warped && wpix_ok) {
+    const float* fp = a.flow + (long long)n * g.fls[0] + (long long)wy * g.fls[2] + wx;
+    const float sx = sample_pos(wx, __ldg(fp), g.W, g.warp_mode, in_x);
+    const float sy = sample_pos(wy, __ldg(fp + g.fls[1]), g.H, g.warp_mode, in_y);
     mytap = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
     const float fx = floorf(sx), fy = floorf(sy);
     wx1 = fx + 1.f - sx; wx0 = sx - fx;
     wy1 = fy + 1.f - sy; wy0 = sy - fy;
+    sx0 = (int)fx; sy0 = (int)fy;
+    sx1 = (sx0 + 1 < g.W) ? sx0 + 1 : sx0;
+    sy1 = (sy0 + 1 < g.H) ? sy0 + 1 : sy0;
   }
 
   const float inv_c = 1.0f / (float)g.C;
   const T* __restrict__ src = (WHICH == 0) ? x2 : x1;
   const long long src_cs = (WHICH == 0) ? g.x2s[1] : g.x1s[1];
+  const long long plane_elems = (long long)g.H * g.W;
+  T* gdst = (T*)((WHICH == 0) ? a.gx1 : a.gx2) + (long long)n * g.C * plane_elems;
 
-  for (int c0 = 0; c0 < g.C; c0 += kCB) {
-    __syncthreads();  // previous chunk fully consumed
-#pragma unroll 2
-    for (int c = 0; c < kCB; ++c) {
-      const int ch = c0 + c;
-      const T* plane = src + (long long)ch * src_cs;
+  for (int c0 = 0; c0 < g.C; c0 += BCH) {
+    __syncthreads();  // G tile complete (first pass) / previous chunk's write-out done
+    if (c0 == 0) BWD_TRACE(WHICH * 32 + 1);
+    // ---- stage 32 channels of the S halo tile, 4 channels of loads in flight per thread
+    if (gather) {
+      for (int cq = 0; cq < BCH; cq += 4) {
+        float tv[4][PPT][4];
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        if (sdst[j] < 0) continue;
-        float v = 0.f;
-        if (ch < g.C && ((valid_mask >> j) & 1u)) {
-          if (WHICH == 0 && warped)
-            v = blend(ldg_f32(plane + taps[j].off[0]), ldg_f32(plane + taps[j].off[1]), ldg_f32(plane + taps[j].off[2]),
-                      ldg_f32(plane + taps[j].off[3]), taps[j]);
-          else
-            v = ldg_f32(plane + taps[j].off[0]);
+        for (int k = 0; k < 4; ++k) {
+          const int ch = min(c0 + cq + k, g.C - 1);  // clamped: always a valid plane (masked below)
+          const T* plane = src + (long long)ch * src_cs;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tv[k][j][q] = ldg_f32(plane + taps[j].off[q]);  // off = 0 for invalid positions
+          }
         }
-        halo[c * (BH_Y * BH_XS) + sdst[j]] = v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const bool ch_ok = c0 + cq + k < g.C;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) {
+            const float r = (ch_ok && ((valid_mask >> j) & 1u)) ? blend(tv[k][j][0], tv[k][j][1], tv[k][j][2], tv[k][j][3], taps[j]) : 0.f;
+            if (sdst[j] >= 0) Ss[(cq + k) * BS_CH + sdst[j]] = r;
+          }
+        }
+      }
+    } else {
+      for (int cq = 0; cq < BCH; cq += 16) {
+        float tv[16][PPT];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int ch = min(c0 + cq + k, g.C - 1);
+          const T* plane = src + (long long)ch * src_cs;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) tv[k][j] = ldg_f32(plane + taps[j].off[0]);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const bool ch_ok = c0 + cq + k < g.C;
+#pragma unroll
+          for (int j = 0; j < PPT; ++j)
+            if (sdst[j] >= 0) Ss[(cq + k) * BS_CH + sdst[j]] = (ch_ok && ((valid_mask >> j) & 1u)) ? tv[k][j] : 0.f;
+        }
       }
     }
     __syncthreads();
-    const int cmax = (g.C - c0) < kCB ? (g.C - c0) : kCB;
-    for (int c = 0; c < cmax; ++c) {
-      const float* hp = halo + c * (BH_Y * BH_XS);
-      float s = 0.f;
+    if (c0 == 0) BWD_TRACE(WHICH * 32 + 2);
+
+    // ---- contraction: acc[cb][px] for channels c0 + cb*8 + subset
+    float acc[4][8];
 #pragma unroll
-      for (int dy = 0; dy < kDb; ++dy) {
+    for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
-        for (int dx = 0; dx < kDb; ++dx) {
-          // halo origin is (iy0-4, ix0-4).  WHICH 0 reads p + d; WHICH 1 reads q - d.
-          const int hy = (WHICH == 0) ? ty + dy : ty + 2 * kMDb - dy;
-          const int hx = (WHICH == 0) ? tx + dx : tx + 2 * kMDb - dx;
-          s = fmaf(G[dy * kDb + dx], hp[hy * BH_XS + hx], s);
-        }
+      for (int px = 0; px < 8; ++px) acc[cb][px] = 0.f;
+#pragma unroll 1
+    for (int dy = 0; dy < kDb; ++dy) {
+      float gv[kDb][8];
+#pragma unroll
+      for (int dx = 0; dx < kDb; ++dx) {
+        const float* gp = Gs + ((dy * kDb + dx) * BT_Y + yrow) * BT_X + strip * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gp);
+        const float4 g1 = *reinterpret_cast<const float4*>(gp + 4);
+        gv[dx][0] = g0.x; gv[dx][1] = g0.y; gv[dx][2] = g0.z; gv[dx][3] = g0.w;
+        gv[dx][4] = g1.x; gv[dx][5] = g1.y; gv[dx][6] = g1.z; gv[dx][7] = g1.w;
       }
-      s *= inv_c;
-      if (!pix_ok) continue;
-      const int ch = c0 + c;
-      if (WHICH == 0) {
-        ((T*)a.gx1)[(long long)n * g.C * g.H * g.W + ((long long)ch * g.H + iy) * g.W + ix] = from_f32<T>(s);
-      } else if (!warped) {
-        ((T*)a.gx2)[(long long)n * g.C * g.H * g.W + ((long long)ch * g.H + iy) * g.W + ix] = from_f32<T>(s);
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        const float* sp = Ss + (cb * 8 + subset) * BS_CH + (yrow + dy) * BS_XS + strip * 8;
+        float sv[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 s4 = *reinterpret_cast<const float4*>(sp + 4 * q);
+          sv[4 * q + 0] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+        }
+#pragma unroll
+        for (int px = 0; px < 8; ++px)
+#pragma unroll
+          for (int dx = 0; dx < kDb; ++dx) acc[cb][px] = fmaf(gv[dx][px], sv[px + dx], acc[cb][px]);
+      }
+    }
+    __syncthreads();  // every thread is done reading the S tile: reuse it as the output stage
+    if (c0 == 0) BWD_TRACE(WHICH * 32 + 3);
+
+    float* Os = Ss;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      float* op = Os + (cb * 8 + subset) * BO_CH + yrow * BT_X + strip * 8;
+      *reinterpret_cast<float4*>(op) = make_float4(acc[cb][0] * inv_c, acc[cb][1] * inv_c, acc[cb][2] * inv_c, acc[cb][3] * inv_c);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(acc[cb][4] * inv_c, acc[cb][5] * inv_c, acc[cb][6] * inv_c, acc[cb][7] * inv_c);
+    }
+    __syncthreads();
+
+    if (c0 == 0) BWD_TRACE(WHICH * 32 + 4);
+    // ---- write-out: one pixel per thread, channels of the chunk
+    if (wpix_ok) {
+      const int cmax = (g.C - c0) < BCH ? (g.C - c0) : BCH;
+      const float* orow = Os + wty * BT_X + wtx;
+      if (!(WHICH == 1 && warped)) {
+        T* gp = gdst + (long long)c0 * plane_elems + (long long)wy * g.W + wx;
+        for (int c = 0; c < cmax; ++c) gp[(long long)c * plane_elems] = from_f32<T>(orow[c * BO_CH]);
       } else {
-        // grad wrt the warped map -> splat into grad_x2, accumulate d/d(position)
-        T* gp = (T*)a.gx2 + (long long)n * g.C * g.H * g.W + (long long)ch * g.H * g.W;
-        const T* xp = x2 + (long long)ch * g.x2s[1];
-        // grad_x2 is contiguous: rebuild tap offsets with the contiguous row stride
-        const int sx0 = mytap.off[0] % (int)g.x2s[2], sy0 = mytap.off[0] / (int)g.x2s[2];
-        const int sx1 = mytap.off[3] % (int)g.x2s[2], sy1 = mytap.off[3] / (int)g.x2s[2];
-        if (mytap.w[0] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx0, s * mytap.w[0]);
-        if (mytap.w[1] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx1, s * mytap.w[1]);
-        if (mytap.w[2] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx0, s * mytap.w[2]);
-        if (mytap.w[3] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx1, s * mytap.w[3]);
         const bool bx1 = sx1 != sx0, by1 = sy1 != sy0;  // far taps inside the image
-        const float v_nw = ldg_f32(xp + mytap.off[0]);
-        const float v_ne = bx1 ? ldg_f32(xp + mytap.off[1]) : 0.f;
-        const float v_sw = by1 ? ldg_f32(xp + mytap.off[2]) : 0.f;
-        const float v_se = (bx1 && by1) ? ldg_f32(xp + mytap.off[3]) : 0.f;
-        gix += s * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
-        giy += s * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
+        // channels in batches of 8: the 32 tap loads of a batch are in flight together
+        for (int cb0 = 0; cb0 < cmax; cb0 += 8) {
+          float tvv[8][4], sv8[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const bool ok = cb0 + k < cmax;
+            const T* xp = x2 + (long long)min(c0 + cb0 + k, g.C - 1) * g.x2s[1];
+            sv8[k] = ok ? orow[(cb0 + k) * BO_CH] : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) tvv[k][q] = ldg_f32(xp + mytap.off[q]);  // clamped taps: always valid
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // taps outside the image contribute nothing to d/d(position)
+            if (!bx1) { tvv[k][1] = 0.f; tvv[k][3] = 0.f; }
+            if (!by1) { tvv[k][2] = 0.f; tvv[k][3] = 0.f; }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (cb0 + k < cmax) {
+              const float s = sv8[k];
+              T* gp = gdst + (long long)(c0 + cb0 + k) * plane_elems;
+              if (mytap.w[0] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx0, s * mytap.w[0]);
+              if (mytap.w[1] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx1, s * mytap.w[1]);
+              if (mytap.w[2] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx0, s * mytap.w[2]);
+              if (mytap.w[3] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx1, s * mytap.w[3]);
+              gix += s * ((tvv[k][1] - tvv[k][0]) * wy1 + (tvv[k][3] - tvv[k][2]) * wy0);
+              giy += s * ((tvv[k][2] - tvv[k][0]) * wx1 + (tvv[k][3] - tvv[k][1]) * wx0);
+            }
+          }
+        }
       }
     }
   }
-  if (WHICH == 1 && warped && pix_ok) {
-    float* gf = a.gflow + (long long)n * 2 * g.H * g.W + (long long)iy * g.W + ix;
+  BWD_TRACE(WHICH * 32 + 5);
+  if (WHICH == 1 && warped && wpix_ok) {
+    float* gf = a.gflow + (long long)n * 2 * plane_elems + (long long)wy * g.W + wx;
     gf[0] = in_x ? gix * pos_scale(g.W, g.warp_mode) : 0.f;
-    gf[(long long)g.H * g.W] = in_y ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
+    gf[plane_elems] = in_y ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
   }
 }
 
@@ -367,6 +487,7 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
   cudaError_t e;
   if (fast) {
     BwdArgs a;
+    a.dbg = get_trace_buffer();
     a.g = g;
     a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out; a.gout = gout;
     a.gx1 = gx1; a.gx2 = gx2; a.gflow = gflow;
@@ -378,8 +499,16 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
       if (e != cudaSuccess) return e;
     }
     dim3 grid(a.tiles_x, a.tiles_y, g.B);
-    corr_bwd_fast_kernel<T, 0><<<grid, 256, 0, stream>>>(a);
-    corr_bwd_fast_kernel<T, 1><<<grid, 256, 0, stream>>>(a);
+    static bool attr_set = false;  // benign race: idempotent
+    if (!attr_set) {
+      e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    corr_bwd_tiled_kernel<T, 0><<<grid, 256, BWD_SMEM, stream>>>(a);
+    corr_bwd_tiled_kernel<T, 1><<<grid, 256, BWD_SMEM, stream>>>(a);
     count_launches(flow != nullptr ? 3 : 2);
     return cudaGetLastError();
   }

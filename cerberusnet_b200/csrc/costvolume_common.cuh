@@ -25,6 +25,9 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 template <typename T> __device__ __forceinline__ float ldg_f32(const T* p) { return to_f32<T>(__ldg(p)); }
+// streaming load that does not allocate in L1 (ld.global.cg): for planes a power-of-two stride
+// apart, which would all fight for the same L1 set
+template <typename T> __device__ __forceinline__ float ldcg_f32(const T* p) { return to_f32<T>(__ldcg(p)); }
 
 // ---------------------------------------------------------------- problem geometry --------
 struct Geom {

@@ -31,7 +31,11 @@ namespace cerb {
 
 static long long* g_trace_buffer = nullptr;  // debugging only
 void set_trace_buffer(long long* p) { g_trace_buffer = p; }
-#define CERB_TRACE(slot) do { if (a.dbg) a.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+long long* get_trace_buffer() { return g_trace_buffer; }
+static int g_trace_iter = 0;
+void set_trace_iter(int it) { g_trace_iter = it; }
+// records only the `dbg_iter`-th tile processed by each CTA (every role keeps its own `titer`)
+#define CERB_TRACE(slot) do { if (a.dbg && titer == a.dbg_iter) a.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------ configuration --------
 constexpr int kMD = 4;
@@ -130,6 +134,7 @@ struct FwdArgs {
   int use_tma_out;  // output tile by TMA store
   int csplit_log2;
   int csplit;       // CTAs per cluster sharing one tile, each taking a slice of the channel chunks (1 = off)
+  int dbg_iter;
   long long* dbg;   // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 64 slots per CTA
 };
 
@@ -202,7 +207,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   if (S > 1) cluster_sync_all();
   const int tile0 = (int)blockIdx.x >> Slog, tile_step = (int)gridDim.x >> Slog;
   const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
-  if (tid == 0) CERB_TRACE(0);
+  int titer = 0;
+  if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 0] = clock64();
 
   int stage = 0;
   uint32_t phase = 0;
@@ -276,6 +282,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           }
         }
         __syncwarp();
+        ++titer;
       }
     } else {
       // ---------------------------- gather warps ----------------------------
@@ -329,6 +336,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
             publish_stage();
           }
+          ++titer;
           continue;
         }
 
@@ -437,6 +445,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             if (++rc == RS) { rc = 0; rcphase ^= 1; }
             publish_stage();
           }
+          ++titer;
           continue;
         }
 
@@ -453,18 +462,19 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           const int chb = gb * kCBatch;
 #pragma unroll
           for (int cb = 0; cb < kCBatch; ++cb) {
-            const int ch = chb + cb;
+            // unconditional loads from always-valid addresses (tap offsets of invalid positions are
+            // 0, channel clamped); validity is applied when the batch is blended -- predicated loads
+            // get consumed one by one (7 predicate registers) and serialise
+            const int ch = min(chb + cb, g.C - 1);
             const T* plane = x2n + (long long)ch * g.x2s[1];
-            const bool ch_ok = ch < g.C;
 #pragma unroll
             for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
-              const bool ok = ch_ok && ((valid_mask >> j) & 1u);
               float* d = &dst[(cb * Cfg::POS_PER_THREAD + j) * 4];
-              d[0] = ok ? ldg_f32(plane + taps[j].off[0]) : 0.f;
+              d[0] = ldg_f32(plane + taps[j].off[0]);
               if (warped) {
-                d[1] = ok ? ldg_f32(plane + taps[j].off[1]) : 0.f;
-                d[2] = ok ? ldg_f32(plane + taps[j].off[2]) : 0.f;
-                d[3] = ok ? ldg_f32(plane + taps[j].off[3]) : 0.f;
+                d[1] = ldg_f32(plane + taps[j].off[1]);
+                d[2] = ldg_f32(plane + taps[j].off[2]);
+                d[3] = ldg_f32(plane + taps[j].off[3]);
               }
             }
           }
@@ -484,7 +494,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
             for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
               const float* v = &cur[(cb * Cfg::POS_PER_THREAD + j) * 4];
-              const float r = warped ? blend(v[0], v[1], v[2], v[3], taps[j]) : v[0];
+              const bool ok = ((valid_mask >> j) & 1u) && (ck * CC + bi * kCBatch + cb < g.C);
+              const float r = !ok ? 0.f : (warped ? blend(v[0], v[1], v[2], v[3], taps[j]) : v[0]);
               if (sdst[j] >= 0) plane_dst[sdst[j]] = r;
             }
           }
@@ -492,6 +503,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
           for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
         }
+        ++titer;
       }
     }
   } else {
@@ -679,11 +691,12 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         named_bar_sync(1, Cfg::NCONS);  // `outs` is rewritten by the next tile's epilogue
       }
       ++tiles_done;
+      ++titer;
     }
     // cluster mates may still be reading this CTA's partial tile: do not exit before they are done
     if (S > 1 && tiles_done > 0) mbar_wait_cluster(done_bar, (uint32_t)((tiles_done - 1) & 1));
     if (S == 1 && a.use_tma_out && tid == 0) tma_store_wait_read0();
-    if (tid == 0) CERB_TRACE(42);
+    if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 42] = clock64();
   }
 }
 
@@ -799,6 +812,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   a.total_tiles = g.B * a.tiles_x * a.tiles_y;
   a.nchunks = (g.C + CC - 1) / CC;
   a.dbg = g_trace_buffer;
+  a.dbg_iter = g_trace_iter;
   CUtensorMap tm_x1, tm_x2, tm_raw, tm_out;
   memset(&tm_x1, 0, sizeof(tm_x1));
   memset(&tm_x2, 0, sizeof(tm_x2));

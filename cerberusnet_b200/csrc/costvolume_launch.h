@@ -33,5 +33,6 @@ cudaError_t launch_flow_warp_backward(int dtype, const void* image, const float*
 
 void count_launches(int n);
 void set_trace_buffer(long long* p);
+void set_trace_iter(int it);
 
 }  // namespace cerb

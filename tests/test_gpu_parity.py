@@ -384,3 +384,27 @@ def test_launch_counter_moves():
     x = torch.randn(1, 8, 16, 32, device=dev())
     ops.warp_corr_forward(x, x, None, 4, 1, 4, 1, 1)
     assert cb.lib().cerb_launch_count() == n0 + 1
+
+
+def test_flow_decoder_harness_trains():
+    """The caller side: a PWC-style decoder on the fused op runs forward and
+    backward, gradients reach the encoder through correlation, warp and flow, and the eval path
+    (cost volume written into the concat buffer) equals the training path."""
+    from cerberusnet_b200.decoder import FlowNetLite, photometric_loss
+    torch.manual_seed(0)
+    net = FlowNetLite().to(dev())
+    img1 = torch.rand(2, 3, 128, 192, device=dev())
+    img2 = torch.rand(2, 3, 128, 192, device=dev())
+    out = net(img1, img2, consistency=True)
+    assert [tuple(f.shape[-2:]) for f in out["flow"]] == [(32, 48), (16, 24), (8, 12), (4, 6), (2, 3)]
+    loss = photometric_loss(img1, img2, out["flow"]) + photometric_loss(img2, img1, out["flow_b"])
+    loss.backward()
+    grads = [p.grad for p in net.parameters()]
+    assert all(g is not None and torch.isfinite(g).all() for g in grads)
+    assert float(net.encoder.stages[0][0][0].weight.grad.abs().sum()) > 0
+    net.eval()
+    with torch.no_grad():
+        ev = net(img1, img2)["flow"][0]
+    with torch.enable_grad():
+        tr = net(img1, img2)["flow"][0]
+    assert rel_err(ev.cpu().numpy(), tr.detach().cpu().numpy()) < 1e-5

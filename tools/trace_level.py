@@ -7,11 +7,16 @@ import bench, cerberusnet_b200 as cb
 from cerberusnet_b200 import ops
 li = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+BATCH = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+TITER = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 C, H, W, wp = bench.PWC_LEVELS[li]
 dev = torch.device("cuda:0")
 lib = cb.lib()
 x1, x2, fl = bench.synth_level(li, C, H, W, wp, 1000, dev)
-out = torch.empty(1, 81, H, W, device=dev)
+x1, x2 = x1.repeat(BATCH, 1, 1, 1), x2.repeat(BATCH, 1, 1, 1)
+fl = fl.repeat(BATCH, 1, 1, 1) if fl is not None else None
+out = torch.empty(BATCH, 81, H, W, device=dev)
+lib.cerb_debug_set_trace_iter(TITER)
 for _ in range(200):
     ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, 0, 0.1, out=out, variant=variant)
 torch.cuda.synchronize()
