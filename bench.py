@@ -303,60 +303,83 @@ def main_gpu(args, rank, world, local_rank):
         "sum_level_us": round(sum(d["us_per_launch"] for d in level_stats), 3),
     }
 
-    # ---- end to end through the host-buffer C ABI: pinned host inputs, H2D + kernel + D2H per level
-    e2e = None
-    if rank == 0 or world > 1:
-        host_sets = []
-        for s in range(2):
-            lv = []
-            for i, (C, H, W, wp) in enumerate(PWC_LEVELS):
-                x1, x2, fl = synth_level(i, C, H, W, wp, 5000 + 100 * s + 7 * rank, "cpu", pin=True)
-                out = torch.empty(1, D2, H, W).pin_memory()
-                lv.append((x1, x2, fl, out))
-            host_sets.append(lv)
-        params, ws_bytes = [], 0
-        for (C, H, W, wp), (x1, x2, fl, out) in zip(PWC_LEVELS, host_sets[0]):
-            p = _lib.make_params(x1, x2, fl, out, PAD, 1, MD, 1, 1, 1, cb.WARP_TORCH, SLOPE)
-            for name in ("x1_stride", "x2_stride", "flow_stride", "out_stride"):
-                setattr(p, name, (ctypes.c_int64 * 4)(0, 0, 0, 0))
-            params.append(p)
-            ws_bytes = max(ws_bytes, lib.cerb_warp_corr_forward_host_workspace(ctypes.byref(p), 1 if wp else 0))
-        # one workspace per level so copies of the next level overlap nothing they should not
-        wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in PWC_LEVELS]
-        h2d = sum(t.numel() * 4 for (x1, x2, fl, _) in host_sets[0] for t in (x1, x2, fl) if t is not None)
-        d2h = sum(out.numel() * 4 for (_, _, _, out) in host_sets[0])
+    # ---- end to end with HOST buffers (pinned): every step copies its inputs host->device and its
+    # results device->host inside the timed region.  Two public entry points are timed:
+    #   (a) cerb_warp_corr_forward_host: the C ABI call, H2D + fused kernel + D2H on one stream;
+    #   (b) cerberusnet_b200.HostPipeline: same work on three streams over double-buffered device
+    #       staging, so the two PCIe directions and the kernels overlap.  (b) is reported as `e2e`.
+    from cerberusnet_b200.host_pipeline import HostPipeline
+    host_sets = []
+    for s in range(2):
+        lv = []
+        for i, (C, H, W, wp) in enumerate(PWC_LEVELS):
+            x1, x2, fl = synth_level(i, C, H, W, wp, 5000 + 100 * s + 7 * rank, "cpu", pin=True)
+            out = torch.empty(1, D2, H, W).pin_memory()
+            lv.append((x1, x2, fl, out))
+        host_sets.append(lv)
+    params, ws_bytes = [], 0
+    for (C, H, W, wp), (x1, x2, fl, out) in zip(PWC_LEVELS, host_sets[0]):
+        p = _lib.make_params(x1, x2, fl, out, PAD, 1, MD, 1, 1, 1, cb.WARP_TORCH, SLOPE)
+        for name in ("x1_stride", "x2_stride", "flow_stride", "out_stride"):
+            setattr(p, name, (ctypes.c_int64 * 4)(0, 0, 0, 0))
+        params.append(p)
+        ws_bytes = max(ws_bytes, lib.cerb_warp_corr_forward_host_workspace(ctypes.byref(p), 1 if wp else 0))
+    wss = [torch.empty(ws_bytes, dtype=torch.uint8, device=dev) for _ in PWC_LEVELS]
+    h2d = sum(t.numel() * 4 for (x1, x2, fl, _) in host_sets[0] for t in (x1, x2, fl) if t is not None)
+    d2h = sum(out.numel() * 4 for (_, _, _, out) in host_sets[0])
 
-        def e2e_step(s):
-            sp = ctypes.c_void_p(stream.cuda_stream)
-            for li, (x1, x2, fl, out) in enumerate(host_sets[s % 2]):
-                rc = lib.cerb_warp_corr_forward_host(ctypes.byref(params[li]), _lib.ptr(x1), _lib.ptr(x2),
-                                                     _lib.ptr(fl), _lib.ptr(out), _lib.ptr(wss[li]), ws_bytes, sp)
-                _lib.check(rc, "cerb_warp_corr_forward_host")
+    def abi_step(s):
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        for li, (x1, x2, fl, out) in enumerate(host_sets[s % 2]):
+            rc = lib.cerb_warp_corr_forward_host(ctypes.byref(params[li]), _lib.ptr(x1), _lib.ptr(x2),
+                                                 _lib.ptr(fl), _lib.ptr(out), _lib.ptr(wss[li]), ws_bytes, sp)
+            _lib.check(rc, "cerb_warp_corr_forward_host")
 
-        k_e2e = max(3, min(args.steps, 200))
+    pipe = HostPipeline(PWC_LEVELS, batch=1, depth=2, device=dev, pad_size=PAD, max_displacement=MD,
+                        warp_mode=cb.WARP_TORCH, leaky_slope=SLOPE)
+
+    pipe.enable_arenas()   # one pinned arena per slot and direction: one memcpy each way per step
+    for s in range(2):
+        for (hx1, hx2, hfl), (x1, x2, fl, _) in zip(pipe.host_inputs(s), host_sets[s]):
+            hx1.copy_(x1); hx2.copy_(x2)
+            if hfl is not None:
+                hfl.copy_(fl)
+
+    def pipe_step(s):
+        pipe.submit_packed(s % 2)
+
+    def time_host_path(step_fn, sync_fn, k):
         for s in range(3):
-            e2e_step(s)
-        torch.cuda.synchronize()
+            step_fn(s)
+        sync_fn()
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
-        with torch.cuda.stream(stream):
-            a.record(stream)
-        for s in range(k_e2e):
-            e2e_step(s)
-        with torch.cuda.stream(stream):
-            b.record(stream)
-        torch.cuda.synchronize()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max(a.elapsed_time(b), wall_ms) / k_e2e  # host-visible completion time
+        for s in range(k):
+            step_fn(s)
+        sync_fn()                       # results are in host memory
+        ms = (time.perf_counter() - t0) * 1e3 / k
         if world > 1:
             import torch.distributed as dist
-            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
-        e2e = {"value": world * IMG_W * IMG_H / (ms_e2e * 1e-3) / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "steps": k_e2e,
-               "api": "cerb_warp_corr_forward_host (pinned host buffers; H2D + fused kernel + D2H per level)"}
+            ms = float(t.item())
+        return ms
+
+    k_e2e = max(3, min(args.steps, 400))
+    ms_abi = time_host_path(abi_step, torch.cuda.synchronize, k_e2e)
+    ms_pipe = time_host_path(pipe_step, pipe.synchronize, k_e2e)
+    # the pipeline's result must be the kernel's result
+    ref_out = ops.warp_corr_forward(*[t.to(dev) for t in host_sets[(k_e2e - 1) % 2][4][:3]], PAD, 1, MD, 1, 1, 1,
+                                    cb.WARP_TORCH, SLOPE)
+    if not torch.equal(ref_out.cpu(), pipe.host_outputs((k_e2e - 1) % 2)[4]):
+        raise RuntimeError("HostPipeline output differs from the device-resident call")
+    e2e = {"value": world * IMG_W * IMG_H / (ms_pipe * 1e-3) / 1e6, "unit": "Mpix/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_pipe, "steps": k_e2e,
+           "api": "cerberusnet_b200.HostPipeline.submit_packed (pinned host arenas; one H2D copy, the fused kernels and "
+                  "one D2H copy per step on three streams, double-buffered); timed host-side until the results "
+                  "are in host memory",
+           "single_stream_c_abi": {"api": "cerb_warp_corr_forward_host", "ms_per_step": ms_abi,
+                                   "value": world * IMG_W * IMG_H / (ms_abi * 1e-3) / 1e6}}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu_baseline = None

@@ -10,6 +10,7 @@ from .correlation import (Correlation, CorrelationFunction, CorrelationTorch, Wa
                           WarpCorrelationFunction, warp_correlation)
 from .flow_warp import FlowWarpFunction, flow_warp, mesh_grid, norm_grid  # noqa: F401
 from .install import install, patch_flow_warp  # noqa: F401
+from .host_pipeline import HostPipeline  # noqa: F401
 from . import ops  # noqa: F401
 
 __version__ = "0.1.0"

@@ -408,3 +408,46 @@ def test_flow_decoder_harness_trains():
     with torch.enable_grad():
         tr = net(img1, img2)["flow"][0]
     assert rel_err(ev.cpu().numpy(), tr.detach().cpu().numpy()) < 1e-5
+
+
+def test_host_pipeline_matches_device_call():
+    """HostPipeline (pinned host buffers, three streams, double-buffered) returns the same bytes as
+    the device-resident call, for both the per-tensor and the packed-arena submission, across
+    slot reuse."""
+    levels = [(24, 8, 16, False), (16, 16, 32, True), (8, 32, 64, True)]
+    pipe = cb.HostPipeline(levels, batch=2, depth=2, device=dev())
+    rs = np.random.RandomState(5)
+
+    def make_inputs():
+        ins = []
+        for (C, H, W, wp) in levels:
+            x1 = torch.from_numpy(rs.standard_normal((2, C, H, W)).astype(np.float32)).pin_memory()
+            x2 = torch.from_numpy(rs.standard_normal((2, C, H, W)).astype(np.float32)).pin_memory()
+            fl = torch.from_numpy((rs.standard_normal((2, 2, H, W)) * 2).astype(np.float32)).pin_memory() if wp else None
+            ins.append((x1, x2, fl))
+        return ins
+
+    def expect(ins):
+        return [ops.warp_corr_forward(a.to(dev()), b.to(dev()), None if f is None else f.to(dev()), 4, 1, 4, 1, 1, 1,
+                                      cb.WARP_TORCH, 0.1).cpu() for (a, b, f) in ins]
+
+    batches = [make_inputs() for _ in range(5)]
+    outs = [[torch.empty(2, 81, H, W).pin_memory() for (_, H, W, _) in levels] for _ in range(5)]
+    for ins, o in zip(batches, outs):
+        pipe.submit(ins, o)
+    pipe.synchronize()
+    for ins, o in zip(batches, outs):
+        for got, want in zip(o, expect(ins)):
+            assert torch.equal(got, want)
+    pipe.enable_arenas()
+    for k in range(4):
+        slot = k % 2
+        pipe.synchronize()  # the arena of this slot is about to be rewritten by the host
+        for (hx1, hx2, hfl), (x1, x2, fl) in zip(pipe.host_inputs(slot), batches[k]):
+            hx1.copy_(x1); hx2.copy_(x2)
+            if hfl is not None:
+                hfl.copy_(fl)
+        pipe.submit_packed(slot)
+        pipe.synchronize()
+        for got, want in zip(pipe.host_outputs(slot), expect(batches[k])):
+            assert torch.equal(got, want)
