@@ -155,8 +155,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Sub-block barrier.  `bar.sync` is `barrier.sync.aligned`: every thread of a warp must execute it
+// convergently, which a warp coming out of an `if (lane == 0)` block does not guarantee (found by
+// compute-sanitizer synccheck).  The non-aligned form counts per-thread arrivals and is safe.
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+  __syncwarp();
+  asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // TMA: 4-D tiled load global -> shared, completion on an mbarrier (SASS: UTMALDG)

@@ -1,0 +1,28 @@
+#!/usr/bin/env python
+"""Small cases that touch every kernel path, for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch
+import cerberusnet_b200 as cb
+from cerberusnet_b200 import ops
+dev = torch.device("cuda:0")
+torch.manual_seed(0)
+def run(B, C, H, W, flow, variant=0, pad=4, sigma=2.0):
+    x1 = torch.randn(B, C, H, W, device=dev); x2 = torch.randn(B, C, H, W, device=dev)
+    fl = torch.randn(B, 2, H, W, device=dev) * sigma if flow else None
+    out = ops.warp_corr_forward(x1, x2, fl, pad, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=variant)
+    g = torch.randn_like(out)
+    ops.warp_corr_backward(x1, x2, fl, out, g, pad, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    torch.cuda.synchronize()
+for flow in (False, True):
+    run(1, 32, 128, 256, flow)            # 8x32 config, TMA everywhere (one tile per CTA)
+    run(2, 20, 24, 64, flow, variant=1)   # 8x32, partial channel chunk, several tiles per CTA not needed
+    run(1, 64, 16, 32, flow)              # 4x16 config with cluster split
+    run(1, 192, 8, 16, flow)              # 4x16, 8-CTA clusters
+    run(3, 7, 9, 50, flow)                # ragged: no TMA (W % 4 != 0)
+    run(2, 12, 26, 28, flow, pad=2)       # pad != md: LDG staging of x1
+run(1, 16, 32, 64, True, sigma=20.0)      # raw box does not fit: direct-gather fallback
+x = torch.randn(1, 6, 12, 20, device=dev); f = torch.randn(1, 2, 12, 20, device=dev) * 3
+o = ops.flow_warp_forward(x, f); ops.flow_warp_backward(x, f, torch.randn_like(o))
+ops.warp_corr_forward(x, x, f, 3, 3, 4, 2, 2); torch.cuda.synchronize()
+print("sanitize cases done")
