@@ -185,6 +185,12 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
+// ---- programmatic dependent launch: the next kernel in the stream may start its launch and setup
+// while this grid is still running; it must not touch global memory produced by its predecessor
+// before pdl_wait() (which returns once the predecessor has completed and flushed).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- thread-block cluster / distributed shared memory
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

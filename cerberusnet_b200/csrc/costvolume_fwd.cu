@@ -209,6 +209,9 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
   int titer = 0;
   if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 0] = clock64();
+  // PDL: everything above (barrier init, descriptor prefetch, cluster sync) overlapped the tail of
+  // the previous kernel in the stream; inputs may be its outputs, so wait before the first read.
+  pdl_wait();
 
   int stage = 0;
   uint32_t phase = 0;
@@ -284,6 +287,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         __syncwarp();
         ++titer;
       }
+      pdl_launch_dependents();  // this role has issued its last copy: let the next kernel start launching
     } else {
       // ---------------------------- gather warps ----------------------------
       const int gt = pt - 32;  // 0 .. kGatherThreads-1
@@ -505,6 +509,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         }
         ++titer;
       }
+      pdl_launch_dependents();
     }
   } else {
     // =========================== CONSUMER WARPS ===========================
@@ -565,6 +570,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (tid == 0) CERB_TRACE(40);
+      if (tile + tile_step >= a.total_tiles) pdl_launch_dependents();  // last tile: only the epilogue is left
 
       // ---------------- epilogue: /C, LeakyReLU, stage tile, TMA store ----------------
       const bool finalize_local = (KS == 1) || (S == 1);  // the cluster split is only used with KS > 1
@@ -858,21 +864,26 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   cfg.blockDim = dim3(Cfg::NTHREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)S;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (S > 1) {
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_x1, tm_x2, tm_raw, tm_out);
-    if (le != cudaSuccess) return le;
-  } else {
-    // no cluster attribute for the plain launch: a 1-CTA "cluster" still switches the CTA scheduler
-    // and costs ~2 us on a one-wave grid
-    kern<<<grid, Cfg::NTHREADS, Cfg::SMEM_BYTES, stream>>>(a, tm_x1, tm_x2, tm_raw, tm_out);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  static const bool use_pdl = getenv("CERB_DEBUG_NO_PDL") == nullptr;
+  if (use_pdl) {  // programmatic dependent launch: our setup overlaps the previous kernel's tail
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
+  if (S > 1) {    // (no cluster attribute for plain launches: a 1-CTA "cluster" still switches the CTA
+                  // scheduler and costs ~2 us on a one-wave grid)
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)S;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_x1, tm_x2, tm_raw, tm_out);
+  if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
 
