@@ -68,7 +68,10 @@ def lib() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.exists(path):
+    override = os.environ.get("CERB_LIB_OVERRIDE")  # kernel A/B experiments (tools/ab_variants.py): an alternative build
+    if override:
+        path = override
+    elif not os.path.exists(path):
         path = _build.build_library()
     L = ctypes.CDLL(path)
     vp, i32, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p

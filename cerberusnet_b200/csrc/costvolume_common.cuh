@@ -65,22 +65,36 @@ __device__ __forceinline__ float div_const(float a, float c, float rc) {
 //   border clip to [0,size-1]               clip_coordinates; grid_sampler.cu:62-64
 // inside = un-clipped position strictly inside (0,size-1) -> gradient passes (ATen
 // clip_coordinates_set_grad), else zero.
-__device__ __forceinline__ float sample_pos(int pix, float disp, int size, int mode, bool& inside, int unnorm_fma = 1) {
-  const float sm1 = (float)(size - 1);
-  const float rsm1 = __frcp_rn(sm1);
+// Per-axis constants of the sample position, computed once per thread (the reciprocal is a
+// MUFU + Newton step + denormal branch: not something to redo for every sample).
+struct AxisConst {
+  float fsize, sm1, rsm1;
+};
+__device__ __forceinline__ AxisConst make_axis(int size) {
+  AxisConst k;
+  k.fsize = (float)size;
+  k.sm1 = (float)(size - 1);
+  k.rsm1 = __frcp_rn(k.sm1);
+  return k;
+}
+
+__device__ __forceinline__ float sample_pos(int pix, float disp, const AxisConst& k, int mode, bool& inside, int unnorm_fma = 1) {
   float v = __fadd_rn((float)pix, disp);
   v = __fmul_rn(2.0f, v);
-  v = (mode == CERB_WARP_TORCH) ? __fmul_rn(v, rsm1) : div_const(v, sm1, rsm1);
+  v = (mode == CERB_WARP_TORCH) ? __fmul_rn(v, k.rsm1) : div_const(v, k.sm1, k.rsm1);
   const float g = __fadd_rn(v, -1.0f);
   float p;
   if (mode == CERB_WARP_TRT)
-    p = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), sm1), 0.5f);  // (.)/2 is exact as *0.5
+    p = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), k.sm1), 0.5f);  // (.)/2 is exact as *0.5
   else
-    p = unnorm_fma ? __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.f), (float)size, -1.f), 0.5f)
-                   : __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), (float)size), -1.f), 0.5f);
-  const float hi = sm1;
-  inside = (p > 0.f) && (p < hi);
-  return fminf(hi, fmaxf(p, 0.f));
+    p = unnorm_fma ? __fmul_rn(__fmaf_rn(__fadd_rn(g, 1.f), k.fsize, -1.f), 0.5f)
+                   : __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(g, 1.f), k.fsize), -1.f), 0.5f);
+  inside = (p > 0.f) && (p < k.sm1);
+  return fminf(k.sm1, fmaxf(p, 0.f));
+}
+
+__device__ __forceinline__ float sample_pos(int pix, float disp, int size, int mode, bool& inside, int unnorm_fma = 1) {
+  return sample_pos(pix, disp, make_axis(size), mode, inside, unnorm_fma);
 }
 
 __device__ __forceinline__ float pos_scale(int size, int mode) {
@@ -200,6 +214,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
@@ -232,6 +248,9 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
   float v;
   asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(cluster_addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void st_dsmem_v4(uint32_t cluster_addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 

@@ -43,7 +43,19 @@ constexpr int kD = 2 * kMD + 1;  // 9
 constexpr int kD2 = kD * kD;     // 81
 constexpr int kProducerThreads = 224;  // 7 staging warps (16 warps total = 4 per SMSP -> 128 regs)
 constexpr int kProducerWarps = kProducerThreads / 32;
-constexpr int kGatherWarps = kProducerWarps - 1;    // warp 0 of the staging warps only issues TMA
+constexpr int kGatherWarps = kProducerWarps - 1;    // one staging warp only issues TMA
+// Which staging warp issues the TMA copies.  It heads the pipeline, so its issue latency matters:
+// measured on the finest PWC level, staging warp 0 (CTA warp 9, on a sub-partition with two
+// consumer warps) 19.0 us vs staging warp 3 (CTA warp 12, sharing a sub-partition with three
+// consumer warps) 22.8 us.
+#ifndef CERB_AB_TMAWARP
+#define CERB_AB_TMAWARP 0
+#endif
+#ifndef CERB_AB_PIPE
+#define CERB_AB_PIPE 1
+#endif
+constexpr int kTmaWarp = CERB_AB_TMAWARP;
+
 constexpr int kGatherThreads = kGatherWarps * 32;
 constexpr int kStages = 3;     // x1 / warped-x2 stages
 constexpr int kRawMargin = 6;  // flow variation (px) inside one halo tile the raw box absorbs
@@ -77,7 +89,9 @@ struct FwdCfg {
   static constexpr size_t SMEM_X2 = SMEM_X1 + sizeof(float) * kStages * X1_STAGE;
   static constexpr size_t SMEM_RAW = (SMEM_X2 + sizeof(float) * kStages * X2_STAGE + 127) / 128 * 128;
   static constexpr size_t SMEM_OUT = (SMEM_RAW + sizeof(float) * RS * RAW_STAGE + 1023) / 1024 * 1024;
-  static constexpr size_t SMEM_RED = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
+  // cluster channel split: slices of the other CTAs' partial tiles are pushed here (KS > 1 only)
+  static constexpr size_t SMEM_RECV = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
+  static constexpr size_t SMEM_RED = SMEM_RECV + (KS > 1 ? sizeof(float) * OUT_TILE : 0);
   static constexpr size_t SMEM_BAR = SMEM_RED + sizeof(int) * 2 * kProducerWarps * 4;  // (kGatherWarps rows used)
   static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * kStages + 2 * RS + 2) * sizeof(uint64_t) + 1024;
   static_assert(NCONS % 32 == 0, "consumer threads must be whole warps");
@@ -173,8 +187,6 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* raw_full = empty_bar + kStages;
   uint64_t* raw_empty = raw_full + RS;
-  uint64_t* part_bar = raw_empty + RS;  // cluster split: every CTA's partial tile is in its shared memory
-  uint64_t* done_bar = part_bar + 1;     // cluster split: every CTA has finished reading the partial tiles
 
   const Geom& g = a.g;
   const int tid = threadIdx.x;
@@ -190,8 +202,6 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], kGatherWarps);
     }
-    mbar_init(part_bar, (uint32_t)a.csplit);
-    mbar_init(done_bar, (uint32_t)a.csplit);
     fence_barrier_init();
     if (a.use_tma_in) tma_prefetch_desc(&tm_x1);
     if (a.use_tma_x2) tma_prefetch_desc(&tm_x2);
@@ -200,11 +210,12 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   }
   __syncthreads();
   // cluster channel split: CTA `crank` of a cluster of `csplit` CTAs handles chunks [ck_begin, ck_end)
-  // of the cluster's tile; remote mbarriers must be initialised before anyone signals them
-  // (csplit is a power of two: shifts, not divisions -- this runs on every thread's critical path)
+  // of the cluster's single tile (csplit is a power of two: shifts, not divisions -- this runs on
+  // every thread's critical path).  The partial tiles meet in the epilogue: each CTA pushes slice r
+  // of its partial tile into CTA r's shared memory, one hardware cluster barrier, each CTA sums
+  // and stores its slice.
   const int S = a.csplit, Slog = a.csplit_log2;
   const int crank = S > 1 ? (int)cluster_ctarank() : 0;
-  if (S > 1) cluster_sync_all();
   const int tile0 = (int)blockIdx.x >> Slog, tile_step = (int)gridDim.x >> Slog;
   const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
   int titer = 0;
@@ -228,7 +239,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const bool reduce_bbox = warped && a.use_tma_raw;
     int red_par = 0;
 
-    if (pwarp == 0) {
+    if (pwarp == kTmaWarp) {
       // ---------------------------- TMA warp ----------------------------
       int ri = 0, xs = 0;
       uint32_t riphase = 0, xphase = 0;
@@ -288,9 +299,11 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         ++titer;
       }
       pdl_launch_dependents();  // this role has issued its last copy: let the next kernel start launching
+      if (S > 1) { __syncwarp(); cluster_sync_all(); }  // pairs with the consumers' barrier (all threads of the cluster arrive)
     } else {
       // ---------------------------- gather warps ----------------------------
-      const int gt = pt - 32;  // 0 .. kGatherThreads-1
+      const int gw = pwarp < kTmaWarp ? pwarp : pwarp - 1;  // 0 .. kGatherWarps-1
+      const int gt = gw * 32 + lane;                        // 0 .. kGatherThreads-1
       int rc = 0;
       uint32_t rcphase = 0;
 
@@ -319,6 +332,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           }
         }
       };
+      const AxisConst axis_x = make_axis(g.W), axis_y = make_axis(g.H);
       auto publish_stage = [&]() {
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
@@ -349,38 +363,50 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         int sdst[Cfg::POS_PER_THREAD];    // smem float offset inside a channel plane, -1 = no position
         unsigned valid_mask = 0;
         int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
+        // every flow vector this thread needs is requested before the first one is used:
+        // unconditional loads from clamped (always valid) addresses -- loads left inside the
+        // validity branches are issued one round trip at a time
+        float fu[Cfg::POS_PER_THREAD], fv[Cfg::POS_PER_THREAD];
+        if (warped) {
+          const float* fn = a.flow + (long long)n * g.fls[0];
+#pragma unroll
+          for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+            const int i = gt + j * kGatherThreads;
+            const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
+            const int cy = min(max(qy0 + hy, 0), g.H - 1), cx = min(max(qx0 + hx, 0), g.W - 1);
+            const float* fp = fn + (long long)cy * g.fls[2] + cx;
+            fu[j] = __ldg(fp);
+            fv[j] = __ldg(fp + g.fls[1]);
+          }
+        }
+        // branch-free per position (selects on validity): the POS_PER_THREAD chains interleave
 #pragma unroll
         for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
           const int i = gt + j * kGatherThreads;
-          sdst[j] = -1;
-          taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = 0;
-          taps[j].w[0] = taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
-          if (i < Cfg::NPOS) {
-            const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
-            sdst[j] = hy * Cfg::XS + hx;
-            const int qy = qy0 + hy, qx = qx0 + hx;
-            if (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) {
-              valid_mask |= 1u << j;
-              if (warped) {
-                const float* fp = a.flow + (long long)n * g.fls[0] + (long long)qy * g.fls[2] + qx;
-                const float u = __ldg(fp), v = __ldg(fp + g.fls[1]);
-                bool in_x, in_y;
-                const float sx = sample_pos(qx, u, g.W, g.warp_mode, in_x);
-                const float sy = sample_pos(qy, v, g.H, g.warp_mode, in_y);
-                taps[j] = make_taps(sx, sy, g.H, g.W, 0);  // hstride 0: off[] = {x0, x1c, x0, x1c}
-                const int y0 = (int)floorf(sy);
-                const int y1c = (y0 + 1 < g.H) ? y0 + 1 : y0;
-                taps[j].off[2] = y0;
-                taps[j].off[3] = y1c;
-              } else {
-                taps[j].off[0] = taps[j].off[1] = qx;
-                taps[j].off[2] = taps[j].off[3] = qy;
-                taps[j].w[0] = 1.f;
-              }
-              xmin = min(xmin, taps[j].off[0]); xmax = max(xmax, taps[j].off[1]);
-              ymin = min(ymin, taps[j].off[2]); ymax = max(ymax, taps[j].off[3]);
-            }
+          const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
+          const int qy = qy0 + hy, qx = qx0 + hx;
+          const bool in_tile = i < Cfg::NPOS;
+          const bool valid = in_tile && qy >= 0 && qy < g.H && qx >= 0 && qx < g.W;
+          const int cy = min(max(qy, 0), g.H - 1), cx = min(max(qx, 0), g.W - 1);
+          sdst[j] = in_tile ? hy * Cfg::XS + hx : -1;
+          float sx = (float)cx, sy = (float)cy;   // un-warped: the pixel itself (weights 1,0,0,0)
+          if (warped) {
+            bool in_x, in_y;
+            sx = sample_pos(cx, fu[j], axis_x, g.warp_mode, in_x);
+            sy = sample_pos(cy, fv[j], axis_y, g.warp_mode, in_y);
           }
+          const Taps tp = make_taps(sx, sy, g.H, g.W, 0);  // hstride 0: off[] = {x0, x1c, x0, x1c}
+          const int y0 = (int)floorf(sy);
+          const int y1c = (y0 + 1 < g.H) ? y0 + 1 : y0;
+          taps[j].off[0] = valid ? tp.off[0] : 0;
+          taps[j].off[1] = valid ? tp.off[1] : 0;
+          taps[j].off[2] = valid ? y0 : 0;
+          taps[j].off[3] = valid ? y1c : 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) taps[j].w[k] = valid ? tp.w[k] : 0.f;
+          if (valid) valid_mask |= 1u << j;
+          xmin = valid ? min(xmin, tp.off[0]) : xmin; xmax = valid ? max(xmax, tp.off[1]) : xmax;
+          ymin = valid ? min(ymin, y0) : ymin; ymax = valid ? max(ymax, y1c) : ymax;
         }
         if (gt == 0) CERB_TRACE(58);
 
@@ -391,8 +417,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
           int* rp = red + red_par * (kGatherWarps * 4);
           if (lane == 0) {
-            rp[(pwarp - 1) * 4 + 0] = xmin; rp[(pwarp - 1) * 4 + 1] = xmax;
-            rp[(pwarp - 1) * 4 + 2] = ymin; rp[(pwarp - 1) * 4 + 3] = ymax;
+            rp[gw * 4 + 0] = xmin; rp[gw * 4 + 1] = xmax;
+            rp[gw * 4 + 2] = ymin; rp[gw * 4 + 3] = ymax;
           }
           named_bar_sync(2, kProducerThreads);
 #pragma unroll
@@ -411,7 +437,9 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           int r0, r1;
           if (path == PATH_RAW) { r0 = (y0 - oy) * Cfg::RAW_W - ox; r1 = (y1c - oy) * Cfg::RAW_W - ox; }
           else { r0 = (int)(y0 * g.x2s[2]); r1 = (int)(y1c * g.x2s[2]); }
-          taps[j].off[0] = r0 + x0; taps[j].off[1] = r0 + x1c; taps[j].off[2] = r1 + x0; taps[j].off[3] = r1 + x1c;
+          const bool ok = (valid_mask >> j) & 1u;  // positions without a sample read offset 0 (always inside the source)
+          taps[j].off[0] = ok ? r0 + x0 : 0; taps[j].off[1] = ok ? r0 + x1c : 0;
+          taps[j].off[2] = ok ? r1 + x0 : 0; taps[j].off[3] = ok ? r1 + x1c : 0;
         }
         if (gt == 0) CERB_TRACE(1);
 
@@ -425,22 +453,41 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             if (gt == 0 && ck < 4) CERB_TRACE(45 + 3 * ck);
             const float* __restrict__ src = raws + rc * Cfg::RAW_STAGE;
             float* __restrict__ x2dst = x2s + stage * Cfg::X2_STAGE;
-            // all taps of one channel are loaded before any result is stored: the loads of the
-            // POS_PER_THREAD samples overlap instead of serialising behind the stores
+            // Software pipeline over channel batches: the taps of batch b+1 are requested before
+            // batch b is blended and stored (the compiler cannot hoist shared loads above shared
+            // stores itself), so a warp never sits out a full LDS round trip per channel.
+            constexpr int CB = Cfg::POS_PER_THREAD >= 4 ? 1 : (Cfg::POS_PER_THREAD >= 2 ? 2 : 4);
+            constexpr int NBAT = CC / CB;
+            // (measured: helps the 4x16 configuration, -0.3 us; neutral to slightly negative for 8x32,
+            //  whose 16 loads per channel already cover the latency)
+            constexpr bool kPipe = CERB_AB_PIPE != 0 && CB > 1;
+            static_assert(CC % CB == 0, "channel batches must divide the stage");
+            float tv[2][CB][Cfg::POS_PER_THREAD][4];
+            auto load_batch = [&](int b, float (&dst)[CB][Cfg::POS_PER_THREAD][4]) {
 #pragma unroll
-            for (int c = 0; c < CC; ++c) {
-              const float* __restrict__ sp = src + c * (Cfg::RAW_H * Cfg::RAW_W);
-              float* __restrict__ dp = x2dst + c * (Cfg::HY * Cfg::XS);
-              float tv[Cfg::POS_PER_THREAD][4];
+              for (int cb = 0; cb < CB; ++cb) {
+                const float* sp = src + (b * CB + cb) * (Cfg::RAW_H * Cfg::RAW_W);
 #pragma unroll
-              for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+                for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tv[j][k] = sp[taps[j].off[k]];  // off = 0 for invalid positions
+                  for (int k = 0; k < 4; ++k) dst[cb][j][k] = sp[taps[j].off[k]];  // off = 0 for invalid positions
+                }
               }
+            };
+            if (kPipe) load_batch(0, tv[0]);
 #pragma unroll
-              for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
-                const float r = ((valid_mask >> j) & 1u) ? blend(tv[j][0], tv[j][1], tv[j][2], tv[j][3], taps[j]) : 0.f;
-                if (sdst[j] >= 0) dp[sdst[j]] = r;
+            for (int b = 0; b < NBAT; ++b) {
+              if (kPipe) { if (b + 1 < NBAT) load_batch(b + 1, tv[(b + 1) & 1]); }
+              else load_batch(b, tv[b & 1]);
+#pragma unroll
+              for (int cb = 0; cb < CB; ++cb) {
+                float* dp = x2dst + (b * CB + cb) * (Cfg::HY * Cfg::XS);
+#pragma unroll
+                for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+                  const float* v = tv[b & 1][cb][j];
+                  const float r = ((valid_mask >> j) & 1u) ? blend(v[0], v[1], v[2], v[3], taps[j]) : 0.f;
+                  if (sdst[j] >= 0) dp[sdst[j]] = r;
+                }
               }
             }
             __syncwarp();
@@ -510,6 +557,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         ++titer;
       }
       pdl_launch_dependents();
+      if (S > 1) { __syncwarp(); cluster_sync_all(); }
     }
   } else {
     // =========================== CONSUMER WARPS ===========================
@@ -574,10 +622,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
       // ---------------- epilogue: /C, LeakyReLU, stage tile, TMA store ----------------
       const bool finalize_local = (KS == 1) || (S == 1);  // the cluster split is only used with KS > 1
-      if (S > 1) {
-        // our partial buffer may still be read by cluster mates (previous tile)
-        if (tiles_done > 0) mbar_wait_cluster(done_bar, (uint32_t)((tiles_done - 1) & 1));
-      } else if (a.use_tma_out) {
+      if (S == 1 && a.use_tma_out) {
         if (tid == 0) tma_store_wait_read0();  // previous tile's store has finished reading `outs`
       }
       named_bar_sync(1, Cfg::NCONS);
@@ -608,53 +653,57 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       if constexpr (KS > 1) {
         named_bar_sync(1, Cfg::NCONS);
         if (tid == 0) CERB_TRACE(37);
-        for (int e = tid; e < Cfg::OUT_TILE; e += Cfg::NCONS) {
-          float s = outs[e];
+        constexpr int kUnits = Cfg::OUT_TILE / 4;       // float4 units of one partial tile
+        const float4* o4 = reinterpret_cast<const float4*>(outs);
+        if (S == 1) {
+          // in-CTA sum of the KS channel groups, finalised in place
+          for (int u = tid; u < kUnits; u += Cfg::NCONS) {
+            float4 s4 = o4[u];
 #pragma unroll
-          for (int k2 = 1; k2 < KS; ++k2) s += outs[k2 * Cfg::OUT_TILE + e];
-          if (finalize_local) {
-            s = div_const(s, divisor, rdivisor);
-            if (g.has_act) s = leaky(s, g.slope);
+            for (int k2 = 1; k2 < KS; ++k2) {
+              const float4 p = o4[k2 * kUnits + u];
+              s4.x += p.x; s4.y += p.y; s4.z += p.z; s4.w += p.w;
+            }
+            float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              sv[k] = div_const(sv[k], divisor, rdivisor);
+              if (g.has_act) sv[k] = leaky(sv[k], g.slope);
+            }
+            reinterpret_cast<float4*>(outs)[u] = make_float4(sv[0], sv[1], sv[2], sv[3]);
           }
-          outs[e] = s;
-        }
-      }
-      if constexpr (KS > 1) if (S > 1) {
-        // ---- cluster reduction of the S partial tiles through distributed shared memory ----
-        if (tid == 0) CERB_TRACE(38);
-        named_bar_sync(1, Cfg::NCONS);            // this CTA's partial tile is complete
-        if (tid < S) {  // one thread per cluster rank: a single cluster-scope fence, then a relaxed arrive each
-          fence_acq_rel_cluster();
-          mbar_arrive_remote_relaxed(mapa_u32(smem_u32(part_bar), (uint32_t)tid));
-        }
-        if (tid == 0) CERB_TRACE(39);
-        mbar_wait_cluster(part_bar, (uint32_t)(tiles_done & 1));
-        const int slice = Cfg::OUT_TILE / S;      // host guarantees divisibility
-        const uint32_t obase = smem_u32(outs);
-        T* outp = (T*)a.out + (long long)n * g.os[0];
-        if (tid == 0) CERB_TRACE(43);
-        // 16-byte remote loads, all issued before the first sum (DSMEM latency ~200 cycles)
-        const int units = slice / 4;                    // float4 units of this CTA's slice
-        constexpr int kUPT = (Cfg::OUT_TILE / 8 + Cfg::NCONS - 1) / Cfg::NCONS;  // S >= 2
-        float4 pv[kUPT][8];
+        } else {
+          // ---- cluster reduction: group sums are pushed to the CTA that owns the slice ----
+          float* recv = (float*)(smem + Cfg::SMEM_RECV);
+          const int units = kUnits >> Slog;             // float4 units per slice (host guarantees divisibility)
+          const uint32_t rbase = smem_u32(recv) + 16u * (uint32_t)(crank * units);
+          for (int u = tid; u < kUnits; u += Cfg::NCONS) {
+            float4 s4 = o4[u];
 #pragma unroll
-        for (int i = 0; i < kUPT; ++i) {
-          const int u = tid + i * Cfg::NCONS;
-          const uint32_t addr = obase + 16u * (uint32_t)(crank * units + u);
-#pragma unroll
-          for (int r = 0; r < 8; ++r)
-            pv[i][r] = (r < S && u < units) ? ld_dsmem_v4(mapa_u32(addr, (uint32_t)r)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < kUPT; ++i) {
-          const int u = tid + i * Cfg::NCONS;
-          if (u < units) {
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) { s4.x += pv[i][r].x; s4.y += pv[i][r].y; s4.z += pv[i][r].z; s4.w += pv[i][r].w; }
+            for (int k2 = 1; k2 < KS; ++k2) {
+              const float4 p = o4[k2 * kUnits + u];
+              s4.x += p.x; s4.y += p.y; s4.z += p.z; s4.w += p.w;
+            }
+            const int r = u / units, idx = u - r * units;
+            st_dsmem_v4(mapa_u32(rbase + 16u * (uint32_t)idx, (uint32_t)r), s4);
+          }
+          if (tid == 0) CERB_TRACE(38);
+          __syncwarp();
+          cluster_arrive_release();                     // my pushes are done ...
+          if (tid == 0) CERB_TRACE(39);
+          cluster_wait_acquire();                       // ... and everyone's have landed here
+          if (tid == 0) CERB_TRACE(43);
+          const float4* r4 = reinterpret_cast<const float4*>(recv);
+          T* outp = (T*)a.out + (long long)n * g.os[0];
+          for (int i = tid; i < units; i += Cfg::NCONS) {
+            float4 s4 = r4[i];
+            for (int r = 1; r < S; ++r) {               // fixed order: results do not depend on timing
+              const float4 p = r4[r * units + i];
+              s4.x += p.x; s4.y += p.y; s4.z += p.z; s4.w += p.w;
+            }
             const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
             // physical chunk -> logical position of the [plane][y][x] tile (undo the partial-tile swizzle)
-            const int pchunk = crank * units + u;
+            const int pchunk = crank * units + i;
             const int row = pchunk / (TX / 4), lchunk = swz_partial<TX>(row, pchunk - row * (TX / 4), true);
             const int plane = row / TY, yy = row - plane * TY;
             const int oy = by0 + yy;
@@ -667,10 +716,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
                 outp[(long long)plane * g.os[1] + (long long)oy * g.os[2] + ox] = from_f32<T>(s);
             }
           }
+          if (tid == 0) CERB_TRACE(41);
         }
-        if (tid == 0) CERB_TRACE(41);
-        named_bar_sync(1, Cfg::NCONS);            // all of this CTA's remote reads are done
-        if (tid < S) mbar_arrive_remote_relaxed(mapa_u32(smem_u32(done_bar), (uint32_t)tid));
       }
       if (S > 1) {
         // output already written by the cluster reduction above
@@ -699,8 +746,6 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       ++tiles_done;
       ++titer;
     }
-    // cluster mates may still be reading this CTA's partial tile: do not exit before they are done
-    if (S > 1 && tiles_done > 0) mbar_wait_cluster(done_bar, (uint32_t)((tiles_done - 1) & 1));
     if (S == 1 && a.use_tma_out && tid == 0) tma_store_wait_read0();
     if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 42] = clock64();
   }

@@ -13,6 +13,10 @@ C, H, W, wp = bench.PWC_LEVELS[li]
 dev = torch.device("cuda:0")
 lib = cb.lib()
 x1, x2, fl = bench.synth_level(li, C, H, W, wp, 1000, dev)
+if os.environ.get("TRACE_FLOW") == "none":
+    fl = None
+elif os.environ.get("TRACE_FLOW") == "zero" and fl is not None:
+    fl = torch.zeros_like(fl)
 x1, x2 = x1.repeat(BATCH, 1, 1, 1), x2.repeat(BATCH, 1, 1, 1)
 fl = fl.repeat(BATCH, 1, 1, 1) if fl is not None else None
 out = torch.empty(BATCH, 81, H, W, device=dev)
