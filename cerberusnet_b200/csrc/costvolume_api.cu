@@ -164,7 +164,8 @@ int cerb_warp_corr_forward(const cerb_corr_params* p, const void* x1, const void
 size_t cerb_warp_corr_backward_workspace(const cerb_corr_params* p, int has_flow) {
   Geom g;
   if (build_geom(p, has_flow != 0, g) != CERB_OK) return 0;
-  if (is_fast(g) || !has_flow) return 0;
+  if (!has_flow) return 0;
+  // the warped second map and the gradient wrt it
   return 2 * (size_t)g.B * g.C * g.H * g.W * dtype_size(p->dtype);
 }
 

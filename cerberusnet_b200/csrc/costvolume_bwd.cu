@@ -7,9 +7,14 @@
 //   GridSampler2DBackward + norm_grid / mesh_grid backward   UnFlowLoss.py:22-32,83-94
 //
 // All batch items in one launch (the reference launches 2*B kernels, .cu:386,407), no padded NHWC
-// scratch, no memsets except grad_x2 when it is splatted through the warp.
+// scratch.  With a flow the backward is warp-forward (re-materialised warped map, workspace) ->
+// two correlation-backward kernels -> warp-backward (atomics into a zeroed grad_x2, flow gradient).
 //
 // Fast path (k=1, s1=s2=1, md=4): corr_bwd_tiled_kernel below, one template for both gradients.
+#include <cstdint>
+#include <cstdlib>
+#include <type_traits>
+
 #include "costvolume_common.cuh"
 #include "costvolume_launch.h"
 
@@ -21,10 +26,8 @@ long long* get_trace_buffer();
 constexpr int kMDb = 4;
 constexpr int kDb = 9;
 constexpr int kD2b = 81;
-constexpr int BT_Y = 8, BT_X = 32;
-constexpr int BH_Y = BT_Y + 2 * kMDb, BH_X = BT_X + 2 * kMDb;  // 16 x 40 halo
-constexpr int BH_XS = BH_X + 1;
-constexpr int kCB = 8;
+constexpr int BT_X = 32;
+constexpr int BH_X = BT_X + 2 * kMDb;  // 40-wide halo
 
 template <typename T> __device__ __forceinline__ void atomic_add_t(T* p, float v);
 template <> __device__ __forceinline__ void atomic_add_t<float>(float* p, float v) { atomicAdd(p, v); }
@@ -34,41 +37,54 @@ template <> __device__ __forceinline__ void atomic_add_t<__nv_bfloat16>(__nv_bfl
 }
 
 struct BwdArgs {
-  long long* dbg;  // optional clock64 trace of CTA 0 (cerb_debug_set_trace_buffer)
+  long long* dbg;  // optional clock64 trace of one CTA (cerb_debug_set_trace_buffer)
   Geom g;
-  const void* x1;
-  const void* x2;
-  const float* flow;
-  const void* out;   // activated forward output (sign only), may be null
+  const void* s[2];        // the "other" operand per gradient: [0] second correlation input (warped x2), [1] x1
+  long long s_ns[2], s_cs[2], s_hs[2];   // its N, C, H strides in elements
+  const void* out;         // activated forward output (sign only), may be null
   const void* gout;
-  void* gx1;
-  void* gx2;
-  float* gflow;
-  int off;           // md - pad
+  void* gdst[2];           // contiguous NCHW gradients: [0] wrt x1, [1] wrt the second correlation input
+  int off;                 // md - pad
   int tiles_x, tiles_y;
+  int async_ok[2];         // fp32 and 16-byte alignment of s[] rows: stage the halo tiles with cp.async
 };
 
-// Register-tiled backward.  Both gradients have the form
+// Register-tiled backward of the correlation.  Both gradients have the form
 //     g[c, q] = 1/C * sum_e  G[e, q] * S[c, q + e],      e in [-4,4]^2
-//   WHICH 0 (grad_x1):  G[e, q] = gO'[e, q]            S = warped x2      (q = x1 pixel)
-//   WHICH 1 (grad_x2w): G[e, q] = gO'[-e, q + e]       S = x1             (q = warped-map pixel)
-// with gO' = grad_out masked by the LeakyReLU of the saved output.  One CTA per 8x32 tile of q:
-//   * the whole G tile (81 planes x 8 x 32, 83 KB) is built once and stays in shared memory;
-//   * 32 channels of the S halo tile (16 x 40, re-warped on the fly for grad_x1) per chunk;
+//   WHICH 0 (grad_x1):     G[e, q] = gO'[e, q]            S = second correlation input   (q = x1 pixel)
+//   WHICH 1 (grad_second): G[e, q] = gO'[-e, q + e]       S = x1                         (q = pixel of the second input)
+// with gO' = grad_out masked by the LeakyReLU of the saved output.  With a flow the second input
+// is the warped map: the launcher materialises it before, and pushes grad_second through the warp
+// backward after, so this kernel is a plain correlation backward.  One CTA per 8x32 tile of q:
+//   * the whole G tile (81 planes x 8 x 32, 83 KB) is fetched once with per-thread asynchronous
+//     copies (all 162 loads of a thread in flight; zero-fill outside the output), the saved output
+//     goes through the not-yet-used S buffer and the LeakyReLU mask is applied in place;
+//   * 32 channels of the S halo tile (16 x 40) per chunk, 16-byte asynchronous copies;
 //   * thread = (8-pixel strip, row, 4 channels): 32 accumulators, per row displacement the 9 x 8
 //     slice of G in registers (LDS.128 broadcast across the 8 channel-subset lanes) and, per
 //     channel, one 16-float row of S (4 LDS.128) -> 72 FFMA;
-//   * results are staged through shared memory and written coalesced; for grad_x2 with a flow
-//     they go straight through the bilinear-warp backward (4 atomics, flow gradient in registers).
+//   * results are staged through shared memory and written coalesced.
 constexpr int BS_XS = 44;                      // S row stride (floats)
-constexpr int BS_CH = BH_Y * BS_XS + 4;        // S channel stride: == 4 (mod 32) -> 8 channels hit 8 bank groups
 constexpr int BCH = 32;                        // channels per chunk
-constexpr int BO_CH = BT_Y * BT_X + 4;         // staged-output channel stride
-constexpr int BG_FLOATS = kD2b * BT_Y * BT_X;  // 20736
-constexpr size_t BWD_SMEM = sizeof(float) * (BG_FLOATS + BCH * BS_CH);
+// TYB rows per tile: 8 (one 256-thread CTA per SM) or 4 (two 128-thread CTAs per SM, so the load
+// phases of one overlap the contraction of the other)
+template <int TYB>
+struct BwdCfg {
+  static constexpr int BT_Y = TYB;
+  static constexpr int BH_Y = TYB + 2 * kMDb;
+  static constexpr int NT = 32 * TYB;                     // threads: one per tile pixel
+  static constexpr int BS_CH = BH_Y * BS_XS + 4;          // S channel stride: 8 channels hit 8 distinct 16-byte bank groups
+  static constexpr int BO_CH = BT_Y * BT_X + 4;           // staged-output channel stride
+  static constexpr int BG_FLOATS = kD2b * BT_Y * BT_X;
+  static constexpr size_t SMEM = sizeof(float) * (BG_FLOATS + BCH * BS_CH);
+  static_assert(BCH * BS_CH >= BG_FLOATS, "the saved-output tile borrows the S buffer");
+};
 
-template <typename T, int WHICH>
-__global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a) {
+template <typename T, int WHICH, int TYB>
+__global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_kernel(const BwdArgs a) {
+  using Cfg = BwdCfg<TYB>;
+  constexpr int BT_Y = Cfg::BT_Y, BH_Y = Cfg::BH_Y, NT = Cfg::NT, BS_CH = Cfg::BS_CH, BO_CH = Cfg::BO_CH,
+                BG_FLOATS = Cfg::BG_FLOATS;
   extern __shared__ __align__(16) float bsm[];
   float* Gs = bsm;                  // [81][8][32]
   float* Ss = bsm + BG_FLOATS;      // [32][BS_CH]   (aliased by the staged output [32][BO_CH])
@@ -76,83 +92,104 @@ __global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a)
   const int tid = threadIdx.x;
   const int n = blockIdx.z;
   const int iy0 = blockIdx.y * BT_Y, ix0 = blockIdx.x * BT_X;
-  const T* __restrict__ x1 = (const T*)a.x1 + (long long)n * g.x1s[0];
-  const T* __restrict__ x2 = (const T*)a.x2 + (long long)n * g.x2s[0];
+  const T* __restrict__ src = (const T*)a.s[WHICH] + (long long)n * a.s_ns[WHICH];
+  const long long src_cs = a.s_cs[WHICH], src_hs = a.s_hs[WHICH];
   const T* __restrict__ gout = (const T*)a.gout + (long long)n * g.os[0];
   const T* __restrict__ outp = a.out ? (const T*)a.out + (long long)n * g.os[0] : nullptr;
-  const bool warped = a.flow != nullptr;
   const bool mask = g.has_act && outp != nullptr;
+  constexpr bool kF32 = std::is_same<T, float>::value;
 
   BWD_TRACE(WHICH * 32 + 0);
-  // ---- G tile: thread = pixel of the tile, planes in batches of 9 (18 independent loads in flight)
+  // ---- G tile: thread = pixel of the tile
   {
     const int ty = tid >> 5, tx = tid & 31;
     const int qy = iy0 + ty, qx = ix0 + tx;
     const bool q_ok = qy < g.H && qx < g.W;
+    if constexpr (kF32) {
+      const uint32_t gs_u32 = smem_u32(Gs) + 4u * (uint32_t)tid, os_u32 = smem_u32(Ss) + 4u * (uint32_t)tid;
+      if (WHICH == 0) {
+        // the same output pixel in every displacement plane: one bounds test, one running offset
+        const int oy = qy - a.off, ox = qx - a.off;
+        const bool ok = q_ok && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
+        const uint32_t nb = ok ? 4u : 0u;
+        const long long o0 = (long long)min(max(oy, 0), g.outH - 1) * g.os[2] + min(max(ox, 0), g.outW - 1);
+        const T* gp = gout + o0;
+        const T* op = mask ? outp + o0 : nullptr;
+#pragma unroll 9
+        for (int plane = 0; plane < kD2b; ++plane) {
+          cp_async4(gs_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), gp, nb);
+          if (mask) { cp_async4(os_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), op, nb); op += g.os[1]; }
+          gp += g.os[1];
+        }
+      } else {
+        // plane (dyi, dxi) reads displacement plane 80 - plane at pixel q + (dyi - 4, dxi - 4):
+        // validity per row / column displacement as bit masks, offsets built incrementally
+        unsigned row_ok = 0, col_ok = 0;
+#pragma unroll
+        for (int d = 0; d < kDb; ++d) {
+          const int py = qy + d - kMDb, px = qx + d - kMDb;
+          if (q_ok && py >= 0 && py < g.H && py - a.off >= 0 && py - a.off < g.outH) row_ok |= 1u << d;
+          if (px >= 0 && px < g.W && px - a.off >= 0 && px - a.off < g.outW) col_ok |= 1u << d;
+        }
+        const int oxc0 = qx - kMDb - a.off;
 #pragma unroll 1
-    for (int dy0 = 0; dy0 < kDb; dy0 += 3) {
-      // Loads are unconditional from clamped (always valid) addresses and validity is applied
-      // afterwards: with only 7 predicate registers the compiler otherwise consumes each predicated
-      // load right after issuing it and the 54 loads serialise.
-      float gvv[3 * kDb], ovv[3 * kDb];
+        for (int dyi = 0; dyi < kDb; ++dyi) {
+          const int oy = min(max(qy + dyi - kMDb - a.off, 0), g.outH - 1);
+          const bool rok = (row_ok >> dyi) & 1u;
+          const long long orow = (long long)(kD2b - 1 - dyi * kDb) * g.os[1] + (long long)oy * g.os[2];
 #pragma unroll
-      for (int r = 0; r < 3 * kDb; ++r) {
-        const int dyi = dy0 + r / kDb, dxi = r % kDb;
-        const int plane = dyi * kDb + dxi;
-        const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
-        const int d = (WHICH == 0) ? plane : (kD2b - 1 - plane);
-        const int oy = min(max(py - a.off, 0), g.outH - 1), ox = min(max(px - a.off, 0), g.outW - 1);
-        const long long o = (long long)d * g.os[1] + (long long)oy * g.os[2] + ox;
-        gvv[r] = ldcg_f32(gout + o);
-        ovv[r] = mask ? ldcg_f32(outp + o) : 1.f;
+          for (int dxi = 0; dxi < kDb; ++dxi) {
+            const int plane = dyi * kDb + dxi;
+            const long long o = orow - (long long)dxi * g.os[1] + min(max(oxc0 + dxi, 0), g.outW - 1);
+            const uint32_t nb = (rok && ((col_ok >> dxi) & 1u)) ? 4u : 0u;
+            cp_async4(gs_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), gout + o, nb);
+            if (mask) cp_async4(os_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), outp + o, nb);
+          }
+        }
       }
-#pragma unroll
-      for (int r = 0; r < 3 * kDb; ++r) {
-        const int dyi = dy0 + r / kDb, dxi = r % kDb;
-        const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
-        const int oy = py - a.off, ox = px - a.off;
-        const bool ok = q_ok && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
-        float v = ok ? gvv[r] : 0.f;
-        if (!(ovv[r] > 0.f)) v *= g.slope;   // ovv == 1 when there is no activation
-        Gs[(dy0 * kDb + r) * (BT_Y * BT_X) + tid] = v;
+      cp_async_commit();
+      cp_async_wait_all();
+      if (mask) {
+        __syncthreads();
+        // LeakyReLU backward in place: every thread masks the elements it copied itself
+#pragma unroll 9
+        for (int plane = 0; plane < kD2b; ++plane) {
+          const int i = plane * (BT_Y * BT_X) + tid;
+          if (!(Ss[i] > 0.f)) Gs[i] *= g.slope;
+        }
       }
-      BWD_TRACE(WHICH * 32 + 6 + dy0 / 3);
-    }
-  }
-
-  // ---- staging plan for the S halo tile: positions handled by this thread (fixed for the tile)
-  constexpr int NPOS = BH_Y * BH_X;
-  constexpr int PPT = (NPOS + 255) / 256;
-  Taps taps[PPT];
-  int sdst[PPT];
-  unsigned valid_mask = 0;
-  const bool gather = (WHICH == 0) && warped;
+    } else {
+#pragma unroll 1
+      for (int dy0 = 0; dy0 < kDb; dy0 += 3) {
+        // Loads are unconditional from clamped (always valid) addresses and validity is applied
+        // afterwards: with only 7 predicate registers the compiler otherwise consumes each predicated
+        // load right after issuing it and the 54 loads serialise.
+        float gvv[3 * kDb], ovv[3 * kDb];
 #pragma unroll
-  for (int j = 0; j < PPT; ++j) {
-    const int i = tid + j * 256;
-    sdst[j] = -1;
-    taps[j].off[0] = taps[j].off[1] = taps[j].off[2] = taps[j].off[3] = 0;
-    taps[j].w[0] = taps[j].w[1] = taps[j].w[2] = taps[j].w[3] = 0.f;
-    if (i < NPOS) {
-      const int hy = i / BH_X, hx = i - hy * BH_X;
-      sdst[j] = hy * BS_XS + hx;
-      const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + hx;
-      if (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) {
-        valid_mask |= 1u << j;
-        if (gather) {
-          const float* fp = a.flow + (long long)n * g.fls[0] + (long long)qy * g.fls[2] + qx;
-          bool in_x, in_y;
-          const float sx = sample_pos(qx, __ldg(fp), g.W, g.warp_mode, in_x);
-          const float sy = sample_pos(qy, __ldg(fp + g.fls[1]), g.H, g.warp_mode, in_y);
-          taps[j] = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
-        } else {
-          const long long hs = (WHICH == 0) ? g.x2s[2] : g.x1s[2];
-          taps[j].off[0] = (int)(qy * hs) + qx;
-          taps[j].w[0] = 1.f;
+        for (int r = 0; r < 3 * kDb; ++r) {
+          const int dyi = dy0 + r / kDb, dxi = r % kDb;
+          const int plane = dyi * kDb + dxi;
+          const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
+          const int d = (WHICH == 0) ? plane : (kD2b - 1 - plane);
+          const int oy = min(max(py - a.off, 0), g.outH - 1), ox = min(max(px - a.off, 0), g.outW - 1);
+          const long long o = (long long)d * g.os[1] + (long long)oy * g.os[2] + ox;
+          gvv[r] = ldcg_f32(gout + o);
+          ovv[r] = mask ? ldcg_f32(outp + o) : 1.f;
+        }
+#pragma unroll
+        for (int r = 0; r < 3 * kDb; ++r) {
+          const int dyi = dy0 + r / kDb, dxi = r % kDb;
+          const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
+          const int oy = py - a.off, ox = px - a.off;
+          const bool ok = q_ok && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
+          float v = ok ? gvv[r] : 0.f;
+          if (!(ovv[r] > 0.f)) v *= g.slope;   // ovv == 1 when there is no activation
+          Gs[(dy0 * kDb + r) * (BT_Y * BT_X) + tid] = v;
         }
       }
     }
   }
+  BWD_TRACE(WHICH * 32 + 6);
 
   // ---- roles
   const int subset = tid & 7, combo = tid >> 3;   // compute: 8 channel subsets x 32 (strip,row) combos
@@ -161,80 +198,64 @@ __global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a)
   const int wy = iy0 + wty, wx = ix0 + wtx;
   const bool wpix_ok = wy < g.H && wx < g.W;
 
-  // grad_x2 with a flow: this pixel's bilinear taps for the splat and the flow gradient
-  Taps mytap;
-  bool in_x = false, in_y = false;
-  float gix = 0.f, giy = 0.f, wx0 = 0.f, wx1 = 0.f, wy0 = 0.f, wy1 = 0.f;
-  int sx0 = 0, sy0 = 0, sx1 = 0, sy1 = 0;
-  if (WHICH == 1 && warped && wpix_ok) {
-    const float* fp = a.flow + (long long)n * g.fls[0] + (long long)wy * g.fls[2] + wx;
-    const float sx = sample_pos(wx, __ldg(fp), g.W, g.warp_mode, in_x);
-    const float sy = sample_pos(wy, __ldg(fp + g.fls[1]), g.H, g.warp_mode, in_y);
-    mytap = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
-    const float fx = floorf(sx), fy = floorf(sy);
-    wx1 = fx + 1.f - sx; wx0 = sx - fx;
-    wy1 = fy + 1.f - sy; wy0 = sy - fy;
-    sx0 = (int)fx; sy0 = (int)fy;
-    sx1 = (sx0 + 1 < g.W) ? sx0 + 1 : sx0;
-    sy1 = (sy0 + 1 < g.H) ? sy0 + 1 : sy0;
-  }
-
   const float inv_c = 1.0f / (float)g.C;
-  const T* __restrict__ src = (WHICH == 0) ? x2 : x1;
-  const long long src_cs = (WHICH == 0) ? g.x2s[1] : g.x1s[1];
   const long long plane_elems = (long long)g.H * g.W;
-  T* gdst = (T*)((WHICH == 0) ? a.gx1 : a.gx2) + (long long)n * g.C * plane_elems;
+  T* gdst = (T*)a.gdst[WHICH] + (long long)n * g.C * plane_elems;
+  const bool async_s = kF32 && a.async_ok[WHICH];
 
   for (int c0 = 0; c0 < g.C; c0 += BCH) {
     __syncthreads();  // G tile complete (first pass) / previous chunk's write-out done
     if (c0 == 0) BWD_TRACE(WHICH * 32 + 1);
-    // ---- stage 32 channels of the S halo tile, 4 channels of loads in flight per thread
-    if (gather) {
-      for (int cq = 0; cq < BCH; cq += 4) {
-        float tv[4][PPT][4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int ch = min(c0 + cq + k, g.C - 1);  // clamped: always a valid plane (masked below)
-          const T* plane = src + (long long)ch * src_cs;
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) tv[k][j][q] = ldg_f32(plane + taps[j].off[q]);  // off = 0 for invalid positions
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const bool ch_ok = c0 + cq + k < g.C;
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) {
-            const float r = (ch_ok && ((valid_mask >> j) & 1u)) ? blend(tv[k][j][0], tv[k][j][1], tv[k][j][2], tv[k][j][3], taps[j]) : 0.f;
-            if (sdst[j] >= 0) Ss[(cq + k) * BS_CH + sdst[j]] = r;
-          }
-        }
+    const int cmax = (g.C - c0) < BCH ? (g.C - c0) : BCH;
+    // ---- stage the S halo tile of this chunk: [cmax][16][40] at (iy0 - 4, ix0 - 4), zero outside the image
+    if (async_s) {
+      constexpr int V4_ROW = BH_X / 4;                 // 10 float4 per halo row
+      constexpr int U = BH_Y * V4_ROW;                 // float4 units per channel
+      // unit index tid, tid + NT, ... decomposed into (channel, unit-in-channel) incrementally
+      int c = tid / U, r = tid - c * U;
+      const uint32_t ss_u32 = smem_u32(Ss);
+      while (c < cmax) {
+        const int hy = r / V4_ROW, v = r - hy * V4_ROW;
+        const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + 4 * v;
+        const bool row_ok = qy >= 0 && qy < g.H && qx >= 0 && qx < g.W;
+        const int nbytes = row_ok ? min(16, 4 * (g.W - qx)) : 0;
+        const T* p = src + (long long)(c0 + c) * src_cs + (long long)(row_ok ? qy : 0) * src_hs + (row_ok ? qx : 0);
+        cp_async16(ss_u32 + 4u * (uint32_t)(c * BS_CH + hy * BS_XS + 4 * v), p, (uint32_t)nbytes);
+        r += NT % U; c += NT / U;
+        if (r >= U) { r -= U; ++c; }
       }
+      cp_async_commit();
+      cp_async_wait_all();
     } else {
-      for (int cq = 0; cq < BCH; cq += 16) {
-        float tv[16][PPT];
+      constexpr int NPOS = BH_Y * BH_X;
+      const int total = cmax * NPOS;
+      for (int u0 = tid; u0 < total; u0 += NT * 8) {
+        float tv[8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int ch = min(c0 + cq + k, g.C - 1);
-          const T* plane = src + (long long)ch * src_cs;
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) tv[k][j] = ldg_f32(plane + taps[j].off[0]);
+        for (int k = 0; k < 8; ++k) {
+          const int u = min(u0 + k * NT, total - 1);
+          const int c = u / NPOS, i = u - c * NPOS;
+          const int hy = i / BH_X, hx = i - hy * BH_X;
+          const int qy = min(max(iy0 - kMDb + hy, 0), g.H - 1), qx = min(max(ix0 - kMDb + hx, 0), g.W - 1);
+          tv[k] = ldg_f32(src + (long long)(c0 + c) * src_cs + (long long)qy * src_hs + qx);
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const bool ch_ok = c0 + cq + k < g.C;
-#pragma unroll
-          for (int j = 0; j < PPT; ++j)
-            if (sdst[j] >= 0) Ss[(cq + k) * BS_CH + sdst[j]] = (ch_ok && ((valid_mask >> j) & 1u)) ? tv[k][j] : 0.f;
+        for (int k = 0; k < 8; ++k) {
+          const int u = u0 + k * NT;
+          if (u < total) {
+            const int c = u / NPOS, i = u - c * NPOS;
+            const int hy = i / BH_X, hx = i - hy * BH_X;
+            const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + hx;
+            Ss[c * BS_CH + hy * BS_XS + hx] = (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) ? tv[k] : 0.f;
+          }
         }
       }
     }
     __syncthreads();
     if (c0 == 0) BWD_TRACE(WHICH * 32 + 2);
 
-    // ---- contraction: acc[cb][px] for channels c0 + cb*8 + subset
+    // ---- contraction: acc[cb][px] for channels c0 + cb*8 + subset (channel groups past C are skipped)
+    const int ncb = (cmax + 7) >> 3;
     float acc[4][8];
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb)
@@ -253,17 +274,19 @@ __global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a)
       }
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
-        const float* sp = Ss + (cb * 8 + subset) * BS_CH + (yrow + dy) * BS_XS + strip * 8;
-        float sv[16];
+        if (cb < ncb) {   // uniform across the CTA
+          const float* sp = Ss + (cb * 8 + subset) * BS_CH + (yrow + dy) * BS_XS + strip * 8;
+          float sv[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sp + 4 * q);
-          sv[4 * q + 0] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+          for (int q = 0; q < 4; ++q) {
+            const float4 s4 = *reinterpret_cast<const float4*>(sp + 4 * q);
+            sv[4 * q + 0] = s4.x; sv[4 * q + 1] = s4.y; sv[4 * q + 2] = s4.z; sv[4 * q + 3] = s4.w;
+          }
+#pragma unroll
+          for (int px = 0; px < 8; ++px)
+#pragma unroll
+            for (int dx = 0; dx < kDb; ++dx) acc[cb][px] = fmaf(gv[dx][px], sv[px + dx], acc[cb][px]);
         }
-#pragma unroll
-        for (int px = 0; px < 8; ++px)
-#pragma unroll
-          for (int dx = 0; dx < kDb; ++dx) acc[cb][px] = fmaf(gv[dx][px], sv[px + dx], acc[cb][px]);
       }
     }
     __syncthreads();  // every thread is done reading the S tile: reuse it as the output stage
@@ -279,54 +302,15 @@ __global__ void __launch_bounds__(256, 1) corr_bwd_tiled_kernel(const BwdArgs a)
     __syncthreads();
 
     if (c0 == 0) BWD_TRACE(WHICH * 32 + 4);
-    // ---- write-out: one pixel per thread, channels of the chunk
+    // ---- write-out: one pixel per thread, channels of the chunk (rows of 32 pixels: coalesced)
     if (wpix_ok) {
-      const int cmax = (g.C - c0) < BCH ? (g.C - c0) : BCH;
       const float* orow = Os + wty * BT_X + wtx;
-      if (!(WHICH == 1 && warped)) {
-        T* gp = gdst + (long long)c0 * plane_elems + (long long)wy * g.W + wx;
-        for (int c = 0; c < cmax; ++c) gp[(long long)c * plane_elems] = from_f32<T>(orow[c * BO_CH]);
-      } else {
-        const bool bx1 = sx1 != sx0, by1 = sy1 != sy0;  // far taps inside the image
-        // channels in batches of 8: the 32 tap loads of a batch are in flight together
-        for (int cb0 = 0; cb0 < cmax; cb0 += 8) {
-          float tvv[8][4], sv8[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const bool ok = cb0 + k < cmax;
-            const T* xp = x2 + (long long)min(c0 + cb0 + k, g.C - 1) * g.x2s[1];
-            sv8[k] = ok ? orow[(cb0 + k) * BO_CH] : 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) tvv[k][q] = ldg_f32(xp + mytap.off[q]);  // clamped taps: always valid
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {  // taps outside the image contribute nothing to d/d(position)
-            if (!bx1) { tvv[k][1] = 0.f; tvv[k][3] = 0.f; }
-            if (!by1) { tvv[k][2] = 0.f; tvv[k][3] = 0.f; }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            if (cb0 + k < cmax) {
-              const float s = sv8[k];
-              T* gp = gdst + (long long)(c0 + cb0 + k) * plane_elems;
-              if (mytap.w[0] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx0, s * mytap.w[0]);
-              if (mytap.w[1] != 0.f) atomic_add_t<T>(gp + sy0 * g.W + sx1, s * mytap.w[1]);
-              if (mytap.w[2] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx0, s * mytap.w[2]);
-              if (mytap.w[3] != 0.f) atomic_add_t<T>(gp + sy1 * g.W + sx1, s * mytap.w[3]);
-              gix += s * ((tvv[k][1] - tvv[k][0]) * wy1 + (tvv[k][3] - tvv[k][2]) * wy0);
-              giy += s * ((tvv[k][2] - tvv[k][0]) * wx1 + (tvv[k][3] - tvv[k][1]) * wx0);
-            }
-          }
-        }
-      }
+      T* gp = gdst + (long long)c0 * plane_elems + (long long)wy * g.W + wx;
+#pragma unroll 8
+      for (int c = 0; c < cmax; ++c) gp[(long long)c * plane_elems] = from_f32<T>(orow[c * BO_CH]);
     }
   }
   BWD_TRACE(WHICH * 32 + 5);
-  if (WHICH == 1 && warped && wpix_ok) {
-    float* gf = a.gflow + (long long)n * 2 * plane_elems + (long long)wy * g.W + wx;
-    gf[0] = in_x ? gix * pos_scale(g.W, g.warp_mode) : 0.f;
-    gf[plane_elems] = in_y ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
-  }
 }
 
 // ------------------------------------------------------------------ generic backward ------
@@ -399,69 +383,102 @@ __global__ void __launch_bounds__(256) corr_bwd_generic_kernel(const Geom g, con
 }
 
 // ------------------------------------------------------------------ stand-alone warp ------
-// flow_warp forward: one thread per (n, y, x), looping channels (coalesced along x).
+// flow_warp forward: one thread per (n, y, x), looping channels (coalesced along x).  `img` and
+// `flow` carry N/C/H strides (W stride 1); the output is contiguous NCHW.
 template <typename T>
-__global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict__ img, const float* __restrict__ flow,
+__global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict__ img, long long in_ns, long long in_cs,
+                                                            long long in_hs, const float* __restrict__ flow,
+                                                            long long f_ns, long long f_cs, long long f_hs,
                                                             T* __restrict__ out, int B, int C, int H, int W, int mode) {
   const long long plane = (long long)H * W;
   const long long total = (long long)B * plane;
+  const AxisConst ax = make_axis(W), ay = make_axis(H);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx / plane);
     const long long rem = idx - (long long)n * plane;
     const int y = (int)(rem / W), x = (int)(rem - (long long)y * W);
-    const float* fp = flow + (long long)n * 2 * plane + rem;
+    const float* fp = flow + (long long)n * f_ns + (long long)y * f_hs + x;
     bool in_x, in_y;
-    const float sx = sample_pos(x, __ldg(fp), W, mode & 3, in_x, !(mode & 4));
-    const float sy = sample_pos(y, __ldg(fp + plane), H, mode & 3, in_y, !(mode & 4));
-    const Taps tp = make_taps(sx, sy, H, W, W);
-    const T* ip = img + (long long)n * C * plane;
+    const float sx = sample_pos(x, __ldg(fp), ax, mode & 3, in_x, !(mode & 4));
+    const float sy = sample_pos(y, __ldg(fp + f_cs), ay, mode & 3, in_y, !(mode & 4));
+    const Taps tp = make_taps(sx, sy, H, W, in_hs);
+    const T* ip = img + (long long)n * in_ns;
     T* op = out + (long long)n * C * plane + rem;
-    for (int c = 0; c < C; ++c) {
-      const T* p = ip + (long long)c * plane;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {   // 16 independent tap loads in flight
+      float v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const T* p = ip + (long long)(c + k) * in_cs;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[k][q] = ldg_f32(p + tp.off[q]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) op[(long long)(c + k) * plane] = from_f32<T>(blend(v[k][0], v[k][1], v[k][2], v[k][3], tp));
+    }
+    for (; c < C; ++c) {
+      const T* p = ip + (long long)c * in_cs;
       op[(long long)c * plane] = from_f32<T>(
           blend(ldg_f32(p + tp.off[0]), ldg_f32(p + tp.off[1]), ldg_f32(p + tp.off[2]), ldg_f32(p + tp.off[3]), tp));
     }
   }
 }
 
-// flow_warp backward: grad_image splatted with atomics (pre-zeroed), grad_flow written.
+// flow_warp backward: grad_image splatted with atomics (pre-zeroed, contiguous), grad_flow written
+// (contiguous); `img` and `flow` carry strides, `gout` is contiguous.
 template <typename T>
-__global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict__ img, const float* __restrict__ flow,
+__global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict__ img, long long in_ns, long long in_cs,
+                                                            long long in_hs, const float* __restrict__ flow,
+                                                            long long f_ns, long long f_cs, long long f_hs,
                                                             const T* __restrict__ gout, T* __restrict__ gimg,
                                                             float* __restrict__ gflow, int B, int C, int H, int W,
                                                             int mode) {
   const long long plane = (long long)H * W;
   const long long total = (long long)B * plane;
+  const AxisConst ax = make_axis(W), ay = make_axis(H);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx / plane);
     const long long rem = idx - (long long)n * plane;
     const int y = (int)(rem / W), x = (int)(rem - (long long)y * W);
-    const float* fp = flow + (long long)n * 2 * plane + rem;
+    const float* fp = flow + (long long)n * f_ns + (long long)y * f_hs + x;
     bool in_x, in_y;
-    const float sx = sample_pos(x, __ldg(fp), W, mode, in_x);
-    const float sy = sample_pos(y, __ldg(fp + plane), H, mode, in_y);
-    const Taps tp = make_taps(sx, sy, H, W, W);
+    const float sx = sample_pos(x, __ldg(fp), ax, mode, in_x);
+    const float sy = sample_pos(y, __ldg(fp + f_cs), ay, mode, in_y);
+    const Taps tp = make_taps(sx, sy, H, W, in_hs);   // reads of img
+    const Taps to = make_taps(sx, sy, H, W, W);       // splat into the contiguous gradient
     const float fx = floorf(sx), fy = floorf(sy);
     const float wx1 = fx + 1.f - sx, wx0 = sx - fx, wy1 = fy + 1.f - sy, wy0 = sy - fy;
     const bool bx1 = (int)fx + 1 < W, by1 = (int)fy + 1 < H;
     float gix = 0.f, giy = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const long long cb = ((long long)n * C + c) * plane;
-      const float gv = ldg_f32(gout + cb + rem);
-      const T* p = img + cb;
-      T* gp = gimg + cb;
-      if (tp.w[0] != 0.f) atomic_add_t<T>(gp + tp.off[0], gv * tp.w[0]);
-      if (tp.w[1] != 0.f) atomic_add_t<T>(gp + tp.off[1], gv * tp.w[1]);
-      if (tp.w[2] != 0.f) atomic_add_t<T>(gp + tp.off[2], gv * tp.w[2]);
-      if (tp.w[3] != 0.f) atomic_add_t<T>(gp + tp.off[3], gv * tp.w[3]);
-      const float v_nw = ldg_f32(p + tp.off[0]);
-      const float v_ne = bx1 ? ldg_f32(p + tp.off[1]) : 0.f;
-      const float v_sw = by1 ? ldg_f32(p + tp.off[2]) : 0.f;
-      const float v_se = (bx1 && by1) ? ldg_f32(p + tp.off[3]) : 0.f;
-      gix += gv * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
-      giy += gv * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
+    const T* ip = img + (long long)n * in_ns;
+    for (int c0 = 0; c0 < C; c0 += 4) {   // 4 channels per batch: 20 independent loads in flight
+      float gv[4], v[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = min(c0 + k, C - 1);
+        gv[k] = ldg_f32(gout + ((long long)n * C + c) * plane + rem);
+        const T* p = ip + (long long)c * in_cs;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[k][q] = ldg_f32(p + tp.off[q]);   // clamped taps: always valid addresses
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (c0 + k < C) {
+          T* gp = gimg + ((long long)n * C + c0 + k) * plane;
+          if (to.w[0] != 0.f) atomic_add_t<T>(gp + to.off[0], gv[k] * to.w[0]);
+          if (to.w[1] != 0.f) atomic_add_t<T>(gp + to.off[1], gv[k] * to.w[1]);
+          if (to.w[2] != 0.f) atomic_add_t<T>(gp + to.off[2], gv[k] * to.w[2]);
+          if (to.w[3] != 0.f) atomic_add_t<T>(gp + to.off[3], gv[k] * to.w[3]);
+          const float v_nw = v[k][0];
+          const float v_ne = bx1 ? v[k][1] : 0.f;
+          const float v_sw = by1 ? v[k][2] : 0.f;
+          const float v_se = (bx1 && by1) ? v[k][3] : 0.f;
+          gix += gv[k] * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
+          giy += gv[k] * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
+        }
+      }
     }
     float* gf = gflow + (long long)n * 2 * plane + rem;
     gf[0] = in_x ? gix * pos_scale(W, mode) : 0.f;
@@ -478,6 +495,24 @@ static int grid_for(long long total, int block) {
   return (int)b;
 }
 
+template <typename T, int TYB>
+static cudaError_t launch_tiled_pair(BwdArgs& a, const Geom& g, cudaStream_t stream) {
+  using Cfg = BwdCfg<TYB>;
+  a.tiles_y = (g.H + TYB - 1) / TYB;
+  dim3 grid(a.tiles_x, a.tiles_y, g.B);
+  static bool attr_set = false;  // benign race: idempotent
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 0, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 1, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  corr_bwd_tiled_kernel<T, 0, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
+  corr_bwd_tiled_kernel<T, 1, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
+  return cudaSuccess;
+}
+
 template <typename T>
 static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, const float* flow, const void* out,
                                 const void* gout, void* gx1, void* gx2, float* gflow, void* workspace,
@@ -486,30 +521,43 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
   const bool fast = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kMDb;
   cudaError_t e;
   if (fast) {
+    // with a flow: the workspace holds the warped map and the gradient wrt it (2 * in_elems of T)
+    T* warped = (T*)workspace;
+    T* gwarped = warped ? warped + in_elems : nullptr;
+    if (flow != nullptr) {
+      if (workspace == nullptr) return cudaErrorInvalidValue;
+      flow_warp_fwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
+          (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], warped, g.B, g.C, g.H, g.W,
+          g.warp_mode);
+    }
+    const long long cs = (long long)g.H * g.W, ns = (long long)g.C * cs;
     BwdArgs a;
     a.dbg = get_trace_buffer();
     a.g = g;
-    a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out; a.gout = gout;
-    a.gx1 = gx1; a.gx2 = gx2; a.gflow = gflow;
+    a.s[0] = flow ? (const void*)warped : x2;
+    a.s_ns[0] = flow ? ns : g.x2s[0]; a.s_cs[0] = flow ? cs : g.x2s[1]; a.s_hs[0] = flow ? (long long)g.W : g.x2s[2];
+    a.s[1] = x1;
+    a.s_ns[1] = g.x1s[0]; a.s_cs[1] = g.x1s[1]; a.s_hs[1] = g.x1s[2];
+    a.out = out; a.gout = gout;
+    a.gdst[0] = gx1;
+    a.gdst[1] = flow ? (void*)gwarped : gx2;
     a.off = g.md - g.pad;
+    for (int w = 0; w < 2; ++w)
+      a.async_ok[w] = std::is_same<T, float>::value && ((uintptr_t)a.s[w] % 16) == 0 && (a.s_ns[w] % 4) == 0 &&
+                      (a.s_cs[w] % 4) == 0 && (a.s_hs[w] % 4) == 0;
     a.tiles_x = (g.W + BT_X - 1) / BT_X;
-    a.tiles_y = (g.H + BT_Y - 1) / BT_Y;
+    static const int force_ty = getenv("CERB_DEBUG_BWD_TY") ? atoi(getenv("CERB_DEBUG_BWD_TY")) : 0;
+    const bool ty4 = force_ty ? force_ty == 4 : true;
+    e = ty4 ? launch_tiled_pair<T, 4>(a, g, stream) : launch_tiled_pair<T, 8>(a, g, stream);
+    if (e != cudaSuccess) return e;
     if (flow != nullptr) {
       e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
       if (e != cudaSuccess) return e;
+      flow_warp_bwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
+          (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
+          g.C, g.H, g.W, g.warp_mode);
     }
-    dim3 grid(a.tiles_x, a.tiles_y, g.B);
-    static bool attr_set = false;  // benign race: idempotent
-    if (!attr_set) {
-      e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
-    corr_bwd_tiled_kernel<T, 0><<<grid, 256, BWD_SMEM, stream>>>(a);
-    corr_bwd_tiled_kernel<T, 1><<<grid, 256, BWD_SMEM, stream>>>(a);
-    count_launches(flow != nullptr ? 3 : 2);
+    count_launches(flow != nullptr ? 5 : 2);
     return cudaGetLastError();
   }
   // generic parameters
@@ -522,17 +570,17 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
   // with a flow: workspace holds the warped map and the gradient wrt it (2 * in_elems of T)
   T* warped = (T*)workspace;
   T* gwarped = warped + in_elems;
-  if (g.x2s[2] != g.W || g.x2s[1] != (long long)g.H * g.W || g.x2s[0] != (long long)g.C * g.H * g.W)
-    return cudaErrorNotSupported;  // generic + flow needs contiguous x2
   flow_warp_fwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-      (const T*)x2, flow, warped, g.B, g.C, g.H, g.W, g.warp_mode);
+      (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], warped, g.B, g.C, g.H, g.W,
+      g.warp_mode);
   corr_bwd_generic_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(
       g, (const T*)x1, warped, (long long)g.C * g.H * g.W, (long long)g.H * g.W, (long long)g.W, (const T*)gout,
       (const T*)out, (T*)gx1, gwarped);
   e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
   if (e != cudaSuccess) return e;
   flow_warp_bwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-      (const T*)x2, flow, gwarped, (T*)gx2, gflow, g.B, g.C, g.H, g.W, g.warp_mode);
+      (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B, g.C,
+      g.H, g.W, g.warp_mode);
   count_launches(4);
   return cudaGetLastError();
 }
@@ -551,8 +599,9 @@ cudaError_t launch_warp_corr_backward(const Geom& g, int dtype, const void* x1, 
 template <typename T>
 static cudaError_t warp_fwd_t(const void* image, const float* flow, void* out, int B, int C, int H, int W, int mode,
                               cudaStream_t stream) {
-  flow_warp_fwd_kernel<T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>((const T*)image, flow, (T*)out, B, C,
-                                                                                    H, W, mode);
+  const long long cs = (long long)H * W;
+  flow_warp_fwd_kernel<T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
+      (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (T*)out, B, C, H, W, mode);
   count_launches(1);
   return cudaGetLastError();
 }
@@ -572,8 +621,10 @@ static cudaError_t warp_bwd_t(const void* image, const float* flow, const void* 
                               int C, int H, int W, int mode, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(gimage, 0, (size_t)B * C * H * W * sizeof(T), stream);
   if (e != cudaSuccess) return e;
+  const long long cs = (long long)H * W;
   flow_warp_bwd_kernel<T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
-      (const T*)image, flow, (const T*)gout, (T*)gimage, gflow, B, C, H, W, mode);
+      (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (const T*)gout, (T*)gimage,
+      gflow, B, C, H, W, mode);
   count_launches(2);
   return cudaGetLastError();
 }

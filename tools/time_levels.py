@@ -15,6 +15,7 @@ ap.add_argument("--batch", type=int, default=1)
 ap.add_argument("--flow", default="iid")
 ap.add_argument("--pyramid", default="pwc")
 ap.add_argument("--sets", type=int, default=0)
+ap.add_argument("--variant", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 B = a.batch
@@ -46,7 +47,7 @@ for li, (C, H, W, wp) in enumerate(PYR[a.pyramid]):
     gr = torch.cuda.CUDAGraph()
     def run():
         for (x1, x2, fl, out) in sets:
-            ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out)
+            ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out, variant=a.variant)
     with torch.cuda.stream(st):
         run(); torch.cuda.synchronize()
         with torch.cuda.graph(gr, stream=st):

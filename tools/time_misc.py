@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Device time of the less common configurations: 16-bit dtypes and max_displacement=8 (KITTI-shaped)."""
+import os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import torch, torch.nn.functional as F
+import cerberusnet_b200 as cb
+from cerberusnet_b200 import ops
+dev = torch.device("cuda:0")
+x = torch.randn(4096, 4096, device=dev); t_end = time.perf_counter() + 1.0
+while time.perf_counter() < t_end: (x @ x).sum().item()
+def timeit(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / reps
+for B in (1, 8):
+    for (C, H, W) in ((32, 128, 256), (64, 64, 128)):
+        for dt in (torch.float32, torch.bfloat16, torch.float16):
+            x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1).to(dt); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1).to(dt)
+            fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+            out = torch.empty(B, 81, H, W, device=dev, dtype=dt)
+            t = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, 0, 0.1, out=out))
+            print(f"fwd B={B} C={C} {H}x{W} {str(dt):16s} {t:8.1f} us")
+# KITTI-shaped: 1242x375 at 1/4 -> 94x311, md=8 (pad 8), batch 32 / 4
+for B in (4, 32):
+    C, H, W = 32, 94, 311
+    x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
+    fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+    t8 = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, 0, 0.1), reps=5)
+    t4 = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, 0, 0.1), reps=5)
+    fl8 = 2 * B * H * W * C * 289
+    print(f"KITTI-shaped B={B} C={C} {H}x{W}: md=8 {t8:9.1f} us ({fl8 / t8 / 1e6:.2f} TFLOP/s)   md=4 {t4:9.1f} us")
