@@ -76,7 +76,10 @@ def test_argument_errors_are_codes_not_aborts():
     assert lib.cerb_flow_warp_forward(None, None, None, 1, 1, 8, 8, 0, 0, None) == -1
     for code in (0, -1, -2, -3, -4, -5, 1, 700):
         assert len(lib.cerb_error_string(code)) > 0
-    assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params()), 1) == 0
+    # with a flow: the re-materialised warped map + the gradient wrt it; without: nothing
+    assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params()), 0) == 0
+    assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params(k=3, pad=5)), 0) == 0
+    assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params()), 1) == 2 * 8 * 16 * 32 * 4
     assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params(k=3, pad=5)), 1) == 2 * 8 * 16 * 32 * 4
 
 
