@@ -64,7 +64,7 @@ static int build_geom(const cerb_corr_params* p, bool has_flow, Geom& g) {
   return CERB_OK;
 }
 
-static bool is_fast(const Geom& g) { return g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == 4; }
+static bool is_fast(const Geom& g) { return g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= 4; }  // forward fast path
 
 }  // namespace cerb
 

@@ -6,7 +6,7 @@
 //     channels_first x2, correlation_forward   correlation_cuda_kernel.cu:13-27, 29-95, 244-324
 //   F.leaky_relu_(out, 0.1)       nnet_training/nnet_models/pwcnet_sfd.py:182
 //
-// Fast path (kernel_size=1, stride1=stride2=1, max_displacement=4: every model in the reference):
+// Fast path (kernel_size=1, stride1=stride2=1, max_displacement>=4; 4 is every model in the reference):
 //   persistent, warp-specialised CTAs, one output tile of TY x TX pixels at a time.
 //   * 3 producer warps: x1 tile per channel chunk by TMA (cp.async.bulk.tensor, zero fill = the
 //     correlation padding) and the (TY+8) x (TX+8) halo tile of the *warped* x2 gathered
@@ -17,6 +17,10 @@
 //     clk/instr, tools/microbench/pipes.cu);
 //   * epilogue: divide by C, LeakyReLU, stage the 81 x TY x TX tile in shared memory (128B
 //     swizzle) and write it with one TMA store.
+//   * max_displacement > 4: the D x D displacement range is covered by 9 x 9 windows (origins 0, 8,
+//     ..., D-9; neighbours overlap by one row/column and write identical values there); a work unit
+//     is (tile, window), the halo tile origin shifts with the window and the output goes out
+//     through a 5-D tensor map (x, y, dx, dy, n).
 // Generic path (any pad/kernel/stride parameters): one thread per output element.
 #include <cuda.h>
 
@@ -140,7 +144,8 @@ struct FwdArgs {
   const float* flow;
   void* out;
   int off;        // md - pad: output pixel (by,bx) looks at input pixel (by+off, bx+off)
-  int tiles_x, tiles_y, total_tiles;
+  int tiles_x, tiles_y, total_tiles;   // total_tiles counts (tile, displacement window) work units
+  int nwin;       // displacement windows per axis (1 for max_displacement 4)
   int nchunks;    // ceil(C / CC)
   int use_tma_in;   // x1 tiles by TMA
   int use_tma_x2;   // un-warped x2 halo tiles by TMA (flow == null)
@@ -166,6 +171,31 @@ template <int TX>
 __device__ __forceinline__ int swz_partial(int row, int chunk, bool on) {
   if constexpr (TX == 16) return on ? (chunk ^ ((row >> 1) & 3)) : chunk;
   else return swz_chunk<TX>(row, chunk);
+}
+
+// work unit -> batch item, displacement-window origin (in [0, D-9]) and tile origin
+struct Unit {
+  int n, woy, wox, by0, bx0;
+};
+template <int TY, int TX>
+__device__ __forceinline__ Unit decode_unit(const FwdArgs& a, int tile) {
+  Unit u;
+  const int per_img = a.tiles_x * a.tiles_y;
+  int t = tile;
+  int win = 0;
+  if (a.nwin > 1) {
+    const int per_win = per_img * a.g.B;
+    win = t / per_win;
+    t -= win * per_win;
+  }
+  u.n = t / per_img;
+  const int trem = t - u.n * per_img;
+  u.by0 = (trem / a.tiles_x) * TY;
+  u.bx0 = (trem % a.tiles_x) * TX;
+  const int wy = win / a.nwin, wx = win - wy * a.nwin;
+  u.woy = min(wy * 8, a.g.D - kD);
+  u.wox = min(wx * 8, a.g.D - kD);
+  return u;
 }
 
 // ------------------------------------------------------------------ fast kernel ----------
@@ -244,11 +274,11 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       int ri = 0, xs = 0;
       uint32_t riphase = 0, xphase = 0;
       for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
-        const int n = tile / (a.tiles_x * a.tiles_y);
-        const int trem = tile - n * (a.tiles_x * a.tiles_y);
-        const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
-        const int iy0 = by0 + a.off, ix0 = bx0 + a.off;
-        const int qy0 = iy0 - kMD, qx0 = ix0 - kMD;
+        const Unit un = decode_unit<TY, TX>(a, tile);
+        const int n = un.n;
+        const int iy0 = un.by0 + a.off, ix0 = un.bx0 + a.off;
+        // halo tile of the second map: displacement window origin w covers displacements w-md .. w-md+8
+        const int qy0 = iy0 + un.woy - g.md, qx0 = ix0 + un.wox - g.md;
         int path = (!warped && a.use_tma_x2) ? PATH_TMA_X2 : PATH_DIRECT, ox = 0, oy = 0;
         // x1 does not depend on the flow: request the first stages' tiles while the gather warps
         // are still computing sample positions and the bounding box
@@ -340,12 +370,11 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       };
 
       for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
-        const int n = tile / (a.tiles_x * a.tiles_y);
-        const int trem = tile - n * (a.tiles_x * a.tiles_y);
-        const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
-        // input-frame origin of the x1 tile and of the x2 halo tile
-        const int iy0 = by0 + a.off, ix0 = bx0 + a.off;
-        const int qy0 = iy0 - kMD, qx0 = ix0 - kMD;
+        const Unit un = decode_unit<TY, TX>(a, tile);
+        const int n = un.n;
+        // input-frame origin of the x1 tile and of the x2 halo tile (shifted with the displacement window)
+        const int iy0 = un.by0 + a.off, ix0 = un.bx0 + a.off;
+        const int qy0 = iy0 + un.woy - g.md, qx0 = ix0 + un.wox - g.md;
 
         // ------------- un-warped second map: the TMA warp loads the halo tile as a box -------------
         if (!warped && a.use_tma_x2) {
@@ -578,9 +607,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     int tiles_done = 0;
     if (tid == 0) CERB_TRACE(16);
     for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
-      const int n = tile / (a.tiles_x * a.tiles_y);
-      const int trem = tile - n * (a.tiles_x * a.tiles_y);
-      const int by0 = (trem / a.tiles_x) * TY, bx0 = (trem % a.tiles_x) * TX;
+      const Unit un = decode_unit<TY, TX>(a, tile);
+      const int n = un.n, by0 = un.by0, bx0 = un.bx0;
 
       float acc[8 * kD];
 #pragma unroll
@@ -705,7 +733,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             // physical chunk -> logical position of the [plane][y][x] tile (undo the partial-tile swizzle)
             const int pchunk = crank * units + i;
             const int row = pchunk / (TX / 4), lchunk = swz_partial<TX>(row, pchunk - row * (TX / 4), true);
-            const int plane = row / TY, yy = row - plane * TY;
+            const int wplane = row / TY, yy = row - wplane * TY;
+            const int plane = (un.woy + wplane / kD) * g.D + un.wox + wplane % kD;   // window plane -> output plane
             const int oy = by0 + yy;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -726,7 +755,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         named_bar_sync(1, Cfg::NCONS);
         if (tid == 0) {
           CERB_TRACE(41);
-          tma_store_4d(&tm_out, outs, bx0, by0, 0, n);
+          tma_store_5d(&tm_out, outs, bx0, by0, un.wox, un.woy, n);
           tma_store_commit();
         }
       } else {
@@ -734,7 +763,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         T* outp = (T*)a.out + (long long)n * g.os[0];
         for (int e = tid; e < Cfg::OUT_TILE; e += Cfg::NCONS) {
           const int row = e / TX, x = e - row * TX;
-          const int plane = row / TY, yy = row - plane * TY;
+          const int wplane = row / TY, yy = row - wplane * TY;
+          const int plane = (un.woy + wplane / kD) * g.D + un.wox + wplane % kD;
           const int oy = by0 + yy, ox = bx0 + x;
           if (oy < g.outH && ox < g.outW) {
             const float v = outs[row * TX + swz_chunk<TX>(row, x >> 2) * 4 + (x & 3)];
@@ -840,6 +870,23 @@ static bool make_tmap_f32(CUtensorMap* tm, const void* base, int W, int H, int C
   return r == CUDA_SUCCESS;
 }
 
+// output as (x, y, dx, dy, n): a 9 x 9 displacement window of a tile is one box
+static bool make_tmap_out5d(CUtensorMap* tm, const void* base, const Geom& g, int bx, int by) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return false;
+  if (((uintptr_t)base & 15) != 0) return false;
+  for (int i = 0; i < 3; ++i)
+    if (g.os[i] <= 0 || (g.os[i] * 4) % 16 != 0) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)g.outW, (cuuint64_t)g.outH, (cuuint64_t)g.D, (cuuint64_t)g.D, (cuuint64_t)g.B};
+  cuuint64_t gstr[4] = {(cuuint64_t)g.os[2] * 4, (cuuint64_t)g.os[1] * 4, (cuuint64_t)g.os[1] * 4 * g.D, (cuuint64_t)g.os[0] * 4};
+  cuuint32_t box[5] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)kD, (cuuint32_t)kD, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bx == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static int num_sms() {
   static int n = []() {
     int dev = 0, v = 0;
@@ -860,7 +907,8 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   a.off = g.md - g.pad;
   a.tiles_x = (g.outW + TX - 1) / TX;
   a.tiles_y = (g.outH + TY - 1) / TY;
-  a.total_tiles = g.B * a.tiles_x * a.tiles_y;
+  a.nwin = (g.D - kD + 7) / 8 + 1;   // 9 x 9 displacement windows per axis: origins 0, 8, ..., D - 9
+  a.total_tiles = g.B * a.tiles_x * a.tiles_y * a.nwin * a.nwin;
   a.nchunks = (g.C + CC - 1) / CC;
   a.dbg = g_trace_buffer;
   a.dbg_iter = g_trace_iter;
@@ -878,12 +926,13 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
     // them with LDG instead.  Raw boxes are aligned by construction.
     if ((tma_mask & 1) && (a.off % 4) == 0)
       a.use_tma_in = make_tmap_f32(&tm_x1, x1, g.W, g.H, g.C, g.B, g.x1s, TX, TY, CC, TX == 32) ? 1 : 0;
-    if ((tma_mask & 4) && (a.off % 4) == 0 && flow == nullptr)
+    // (x2 halo tiles start at bx0 - pad + window origin; origins are multiples of 8 and D - 9 = 2 md - 8)
+    if ((tma_mask & 4) && (g.pad % 4) == 0 && (a.nwin == 1 || (g.md % 2) == 0) && flow == nullptr)
       a.use_tma_x2 = make_tmap_f32(&tm_x2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::XS, Cfg::HY, CC, false) ? 1 : 0;
     if ((tma_mask & 8) && flow != nullptr)
       a.use_tma_raw = make_tmap_f32(&tm_raw, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W, Cfg::RAW_H, CC, false) ? 1 : 0;
     if (tma_mask & 2)
-      a.use_tma_out = make_tmap_f32(&tm_out, out, g.outW, g.outH, g.D2, g.B, g.os, TX, TY, kD2, TX == 32) ? 1 : 0;
+      a.use_tma_out = make_tmap_out5d(&tm_out, out, g, TX, TY) ? 1 : 0;
   }
   auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS>;
   static bool attr_set = false;  // benign race: the attribute call is idempotent
@@ -935,13 +984,14 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
 template <typename T>
 static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
                                 int variant, cudaStream_t stream) {
-  const bool fast_ok = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kMD && variant != CERB_FWD_VARIANT_GENERIC;
+  const bool fast_ok = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= kMD && variant != CERB_FWD_VARIANT_GENERIC;
   if (fast_ok) {
     const int no_tma = (variant == CERB_FWD_VARIANT_FAST_NOTMA || variant == CERB_FWD_VARIANT_SMALL_NOTMA) ? 1 : 0;
     bool small = variant == CERB_FWD_VARIANT_SMALL || variant == CERB_FWD_VARIANT_SMALL_NOTMA;
     if (variant == CERB_FWD_VARIANT_AUTO) {
       // not enough 8x32 tiles to fill the GPU: 4x16 tiles with the channels split four ways in-CTA
-      const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8);
+      const long long nwin = (g.D - kD + 7) / 8 + 1;
+      const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8) * nwin * nwin;
       small = big_tiles < (long long)num_sms() * 3 / 4;
     }
     if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, true, stream);

@@ -146,6 +146,21 @@ def test_general_parameters_vs_oracle(p, k, md, s1, s2, with_flow):
         assert rel_err(gf.cpu().numpy(), rf) < TOL
 
 
+@pytest.mark.parametrize("p,md", [(8, 8), (4, 10), (5, 5), (6, 6), (7, 7), (12, 12), (4, 8)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("with_flow", [False, True])
+def test_large_displacement_windows_vs_oracle(p, md, variant, with_flow):
+    """max_displacement > 4 on the fast kernels: the D x D range is tiled by 9 x 9 displacement
+    windows (BASELINE configs[4]: md = 8; the reference's __main__ case pad 4 / md 10)."""
+    x1, x2, fl = rand_case(23 + md, 2, 12, 30, 40)
+    flow = fl if with_flow else None
+    ref = co.level_forward(x1, x2, flow, p, 1, md, 1, 1, co.WARP_TORCH, 0.1)
+    t1, t2, tf = to_dev(x1, x2, flow)
+    out = ops.warp_corr_forward(t1, t2, tf, p, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=variant)
+    assert out.shape == ref.shape
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+
+
 def test_flow_far_outside_every_border():
     """Samples clipped at all four borders (stress set of SURVEY.md 8d: |flow| up to 3*md and
     beyond): border clamp identical to ATen clip_coordinates, zero flow-gradient where clipped."""

@@ -23,12 +23,15 @@ for B in (1, 8):
             out = torch.empty(B, 81, H, W, device=dev, dtype=dt)
             t = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, 0, 0.1, out=out))
             print(f"fwd B={B} C={C} {H}x{W} {str(dt):16s} {t:8.1f} us")
-# KITTI-shaped: 1242x375 at 1/4 -> 94x311, md=8 (pad 8), batch 32 / 4
-for B in (4, 32):
-    C, H, W = 32, 94, 311
-    x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
-    fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
-    t8 = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, 0, 0.1), reps=5)
-    t4 = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, 0, 0.1), reps=5)
-    fl8 = 2 * B * H * W * C * 289
-    print(f"KITTI-shaped B={B} C={C} {H}x{W}: md=8 {t8:9.1f} us ({fl8 / t8 / 1e6:.2f} TFLOP/s)   md=4 {t4:9.1f} us")
+# BASELINE configs[4] / SURVEY 8d config 5: KITTI-shaped pairs padded to 1280x384 (PWC pyramid) or 1248x384 (HRNet),
+# finest level, max_displacement = pad = 8 (289 planes), batch sweep
+for (C, H, W) in ((32, 96, 320), (48, 96, 312)):
+    for B in (1, 4, 32):
+        x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
+        fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+        out = torch.empty(B, 289, H, W, device=dev)
+        t8 = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, 0, 0.1, out=out), reps=5)
+        tg = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, 0, 0.1, out=out, variant=5), reps=2)
+        fl8 = 2 * B * H * W * C * 289
+        by8 = B * H * W * 4 * (2 * C + 289 + 2)
+        print(f"md=8 B={B} C={C} {H}x{W}: windowed fast path {t8:9.1f} us ({fl8 / t8 / 1e6:5.2f} TFLOP/s, {by8 / t8 / 1e3:6.0f} GB/s)   generic kernel {tg:9.1f} us")
