@@ -85,6 +85,12 @@ struct FwdCfg {
   // (W/(W-1)) stretch of the training-path warp, and 3 columns so the box can start 16B-aligned
   static constexpr int RAW_H = HY + 2 * kRawMargin + 2;
   static constexpr int RAW_W = (HX + 2 * kRawMargin + 2 + 3 + 3) / 4 * 4;
+  // 16-bit inputs: the raw box and the x1 tile arrive by TMA as 16-bit data inside one raw stage
+  // (box rows padded to 16 bytes, the x1 tile behind the box); the gather warps convert
+  static constexpr int RAW_W16 = (RAW_W + 7) / 8 * 8;
+  static constexpr int RAW16_BOX_BYTES = CC * RAW_H * RAW_W16 * 2;
+  static constexpr int RAW16_X1_OFF = (RAW16_BOX_BYTES + 127) / 128 * 128;   // bytes
+  static constexpr int RAW16_X1_BYTES = CC * TY * TX * 2;
   static constexpr int X1_STAGE = CC * TY * TX;       // floats
   static constexpr int X2_STAGE = CC * HY * XS;       // floats
   static constexpr int RAW_STAGE = CC * RAW_H * RAW_W;  // floats
@@ -102,6 +108,7 @@ struct FwdCfg {
   static_assert((sizeof(float) * X1_STAGE) % 1024 == 0, "x1 stage must keep 1024-byte alignment");
   static_assert((sizeof(float) * X2_STAGE) % 128 == 0 && (sizeof(float) * RAW_STAGE) % 128 == 0, "TMA dst alignment");
   static_assert(CC % KS == 0, "channel groups must divide the stage");
+  static_assert(RAW16_X1_OFF + RAW16_X1_BYTES <= (int)sizeof(float) * RAW_STAGE, "16-bit box + x1 tile must fit a raw stage");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
@@ -151,6 +158,8 @@ struct FwdArgs {
   int use_tma_x2;   // un-warped x2 halo tiles by TMA (flow == null)
   int use_tma_raw;  // raw x2 source boxes by TMA, warp gathered from shared memory
   int use_tma_out;  // output tile by TMA store
+  int raw16;        // 16-bit inputs: raw x2 box and x1 tile by TMA as 16-bit data, converted by the gather warps
+  int out_vec8;     // 16-bit output: 16-byte stores straight from the staged tile
   int csplit_log2;
   int csplit;       // CTAs per cluster sharing one tile, each taking a slice of the channel chunks (1 = off)
   int dbg_iter;
@@ -266,7 +275,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const int pwarp = pt >> 5;
     const int lane = pt & 31;
     const bool warped = a.flow != nullptr;
-    const bool reduce_bbox = warped && a.use_tma_raw;
+    const bool raw16 = sizeof(T) == 2 && a.raw16;           // 16-bit inputs staged through the raw stage
+    const bool reduce_bbox = (warped || raw16) && a.use_tma_raw;
     int red_par = 0;
 
     if (pwarp == kTmaWarp) {
@@ -303,14 +313,22 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           red_par ^= 1;
           ox = xmin & ~3;
           oy = ymin;
-          if (xmin <= xmax && xmax - ox < Cfg::RAW_W && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+          if (raw16) ox = xmin & ~7;
+          if (xmin <= xmax && xmax - ox < (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W) && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
         }
         if (lane == 0) {
           for (int ck = ck_begin; ck < ck_end; ++ck) {
             if (path == PATH_RAW) {
               mbar_wait(&raw_empty[ri], riphase ^ 1);
-              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
-              tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
+              if (raw16) {
+                unsigned char* rs = (unsigned char*)(raws + ri * Cfg::RAW_STAGE);
+                mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(Cfg::RAW16_BOX_BYTES + Cfg::RAW16_X1_BYTES));
+                tma_load_4d(rs, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
+                tma_load_4d(rs + Cfg::RAW16_X1_OFF, &tm_x1, &raw_full[ri], ix0, iy0, ck * CC, n);
+              } else {
+                mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
+                tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
+              }
               if (++ri == RS) { ri = 0; riphase ^= 1; }
             }
             if (ck - ck_begin < x1_pre) continue;  // x1 tile already requested above
@@ -456,15 +474,16 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             ymin = min(ymin, rp[w * 4 + 2]); ymax = max(ymax, rp[w * 4 + 3]);
           }
           red_par ^= 1;
-          ox = xmin & ~3;  // TMA box starts must be 16-byte aligned
+          ox = raw16 ? (xmin & ~7) : (xmin & ~3);  // TMA box starts must be 16-byte aligned
           oy = ymin;
-          if (xmin <= xmax && xmax - ox < Cfg::RAW_W && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+          if (xmin <= xmax && xmax - ox < (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W) && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
         }
 #pragma unroll
         for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
           const int x0 = taps[j].off[0], x1c = taps[j].off[1], y0 = taps[j].off[2], y1c = taps[j].off[3];
           int r0, r1;
-          if (path == PATH_RAW) { r0 = (y0 - oy) * Cfg::RAW_W - ox; r1 = (y1c - oy) * Cfg::RAW_W - ox; }
+          const int raw_w = raw16 ? Cfg::RAW_W16 : Cfg::RAW_W;
+          if (path == PATH_RAW) { r0 = (y0 - oy) * raw_w - ox; r1 = (y1c - oy) * raw_w - ox; }
           else { r0 = (int)(y0 * g.x2s[2]); r1 = (int)(y1c * g.x2s[2]); }
           const bool ok = (valid_mask >> j) & 1u;  // positions without a sample read offset 0 (always inside the source)
           taps[j].off[0] = ok ? r0 + x0 : 0; taps[j].off[1] = ok ? r0 + x1c : 0;
@@ -476,12 +495,52 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           // ------------- warp gathered from the raw source box in shared memory -------------
           for (int ck = ck_begin; ck < ck_end; ++ck) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
+            if (!a.use_tma_in && !raw16) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
             if (gt == 0 && ck < 4) CERB_TRACE(44 + 3 * ck);
             mbar_wait(&raw_full[rc], rcphase);
             if (gt == 0 && ck < 4) CERB_TRACE(45 + 3 * ck);
             const float* __restrict__ src = raws + rc * Cfg::RAW_STAGE;
             float* __restrict__ x2dst = x2s + stage * Cfg::X2_STAGE;
+            if constexpr (sizeof(T) == 2) {
+              if (raw16) {
+                // x1 tile: 16-bit [c][y][x] behind the box -> fp32 stage in the consumers' swizzled layout
+                const unsigned char* rs = (const unsigned char*)src;
+                const uint4* x1r = reinterpret_cast<const uint4*>(rs + Cfg::RAW16_X1_OFF);
+                float* x1dst = x1s + stage * Cfg::X1_STAGE;
+                for (int e8 = gt; e8 < Cfg::X1_STAGE / 8; e8 += kGatherThreads) {
+                  const uint4 pk = x1r[e8];
+                  const T* hv = reinterpret_cast<const T*>(&pk);
+                  const int e = e8 * 8, row = e / TX, x = e - row * TX;   // row = c * TY + y
+                  float4 lo = make_float4(to_f32<T>(hv[0]), to_f32<T>(hv[1]), to_f32<T>(hv[2]), to_f32<T>(hv[3]));
+                  float4 hi = make_float4(to_f32<T>(hv[4]), to_f32<T>(hv[5]), to_f32<T>(hv[6]), to_f32<T>(hv[7]));
+                  *reinterpret_cast<float4*>(x1dst + row * TX + swz_chunk<TX>(row, x >> 2) * 4) = lo;
+                  *reinterpret_cast<float4*>(x1dst + row * TX + swz_chunk<TX>(row, (x >> 2) + 1) * 4) = hi;
+                }
+                // taps from the 16-bit box
+                const T* __restrict__ src16 = reinterpret_cast<const T*>(rs);
+#pragma unroll
+                for (int c = 0; c < CC; ++c) {
+                  const T* __restrict__ sp = src16 + c * (Cfg::RAW_H * Cfg::RAW_W16);
+                  float* __restrict__ dp = x2dst + c * (Cfg::HY * Cfg::XS);
+                  float tv16[Cfg::POS_PER_THREAD][4];
+#pragma unroll
+                  for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) tv16[j][k] = to_f32<T>(sp[taps[j].off[k]]);
+                  }
+#pragma unroll
+                  for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+                    const float r = ((valid_mask >> j) & 1u) ? blend(tv16[j][0], tv16[j][1], tv16[j][2], tv16[j][3], taps[j]) : 0.f;
+                    if (sdst[j] >= 0) dp[sdst[j]] = r;
+                  }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&raw_empty[rc]);
+                if (++rc == RS) { rc = 0; rcphase ^= 1; }
+                publish_stage();
+                continue;
+              }
+            }
             // Software pipeline over channel batches: the taps of batch b+1 are requested before
             // batch b is blended and stored (the compiler cannot hoist shared loads above shared
             // stores itself), so a warp never sits out a full LDS round trip per channel.
@@ -758,6 +817,32 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           tma_store_5d(&tm_out, outs, bx0, by0, un.wox, un.woy, n);
           tma_store_commit();
         }
+      } else if (sizeof(T) == 2 && a.out_vec8) {
+        // 16-bit output: 8 pixels (16 bytes) per store from the staged fp32 tile
+        named_bar_sync(1, Cfg::NCONS);
+        T* outp = (T*)a.out + (long long)n * g.os[0];
+        for (int u = tid; u < Cfg::OUT_TILE / 8; u += Cfg::NCONS) {
+          const int row = u / (TX / 8), xg = u - row * (TX / 8);
+          const int wplane = row / TY, yy = row - wplane * TY;
+          const int plane = (un.woy + wplane / kD) * g.D + un.wox + wplane % kD;
+          const int oy = by0 + yy, ox = bx0 + xg * 8;
+          if (oy < g.outH && ox < g.outW) {
+            const float4 lo = *reinterpret_cast<const float4*>(outs + row * TX + swz_chunk<TX>(row, xg * 2) * 4);
+            const float4 hi = *reinterpret_cast<const float4*>(outs + row * TX + swz_chunk<TX>(row, xg * 2 + 1) * 4);
+            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            T* gp = outp + (long long)plane * g.os[1] + (long long)oy * g.os[2] + ox;
+            if (ox + 8 <= g.outW) {
+              uint4 pk;
+              T* hv = reinterpret_cast<T*>(&pk);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) hv[k] = from_f32<T>(v[k]);
+              *reinterpret_cast<uint4*>(gp) = pk;
+            } else {
+              for (int k = 0; k < 8 && ox + k < g.outW; ++k) gp[k] = from_f32<T>(v[k]);
+            }
+          }
+        }
+        named_bar_sync(1, Cfg::NCONS);  // `outs` is rewritten by the next tile's epilogue
       } else {
         named_bar_sync(1, Cfg::NCONS);
         T* outp = (T*)a.out + (long long)n * g.os[0];
@@ -852,22 +937,27 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // fp32 NCHW (W-stride 1) tensor map with box {bx, by, bc, 1}
-static bool make_tmap_f32(CUtensorMap* tm, const void* base, int W, int H, int C, int B, const long long strides[3],
-                          int bx, int by, int bc, bool swizzle128) {
+// 4-D (x, y, c, n) tiled tensor map over an NCHW tensor of `esize`-byte elements
+static bool make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
+                      const long long strides[3], int bx, int by, int bc, bool swizzle128) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
   if (((uintptr_t)base & 15) != 0) return false;
   for (int i = 0; i < 3; ++i)
-    if (strides[i] <= 0 || (strides[i] * 4) % 16 != 0) return false;
-  if (bx > 256 || by > 256 || bc > 256) return false;
+    if (strides[i] <= 0 || (strides[i] * esize) % 16 != 0) return false;
+  if (bx > 256 || by > 256 || bc > 256 || (bx * esize) % 16 != 0) return false;
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-  cuuint64_t gstr[3] = {(cuuint64_t)strides[2] * 4, (cuuint64_t)strides[1] * 4, (cuuint64_t)strides[0] * 4};
+  cuuint64_t gstr[3] = {(cuuint64_t)strides[2] * esize, (cuuint64_t)strides[1] * esize, (cuuint64_t)strides[0] * esize};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bc, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, dt, 4, const_cast<void*>(base), dims, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+static bool make_tmap_f32(CUtensorMap* tm, const void* base, int W, int H, int C, int B, const long long strides[3],
+                          int bx, int by, int bc, bool swizzle128) {
+  return make_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, W, H, C, B, strides, bx, by, bc, swizzle128);
 }
 
 // output as (x, y, dx, dy, n): a 9 x 9 displacement window of a tile is one box
@@ -934,6 +1024,19 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
     if (tma_mask & 2)
       a.use_tma_out = make_tmap_out5d(&tm_out, out, g, TX, TY) ? 1 : 0;
   }
+  a.raw16 = a.out_vec8 = 0;
+  if (sizeof(T) == 2 && !force_no_tma && (tma_mask & 8)) {
+    // 16-bit inputs: raw x2 box and x1 tile by TMA as 16-bit data (box starts 16-byte aligned: multiples of 8 elements)
+    const CUtensorMapDataType dt = std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if ((a.off % 8) == 0 &&
+        make_tmap(&tm_raw, dt, 2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W16, Cfg::RAW_H, CC, false) &&
+        make_tmap(&tm_x1, dt, 2, x1, g.W, g.H, g.C, g.B, g.x1s, TX, TY, CC, false)) {
+      a.raw16 = 1;
+      a.use_tma_raw = 1;
+    }
+  }
+  if (sizeof(T) == 2)
+    a.out_vec8 = (((uintptr_t)out & 15) == 0 && g.os[0] % 8 == 0 && g.os[1] % 8 == 0 && g.os[2] % 8 == 0) ? 1 : 0;
   auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS>;
   static bool attr_set = false;  // benign race: the attribute call is idempotent
   if (!attr_set) {

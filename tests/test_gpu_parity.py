@@ -190,10 +190,33 @@ def test_half_precision_io(dtype, tol, with_flow):
     h1, h2 = t1.to(dtype), t2.to(dtype)
     ref = co.level_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), fl if with_flow else None, 4, 1, 4, 1, 1,
                            co.WARP_TORCH, 0.1)
-    for v in (0, 3, 5):
+    for v in (0, 1, 2, 3, 4, 5):
         out = ops.warp_corr_forward(h1, h2, tf, 4, 1, 4, 1, 1, 1, 0, 0.1, variant=v)
         assert out.dtype == dtype
         assert rel_err(out.float().cpu().numpy(), ref) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("shape", [(1, 32, 40, 72), (2, 12, 19, 37), (1, 8, 64, 128), (1, 16, 24, 44)])
+@pytest.mark.parametrize("flow_kind", ["none", "iid", "big"])
+def test_half_precision_tma_paths(dtype, tol, shape, flow_kind):
+    """16-bit TMA staging (raw box + x1 tile as 16-bit data, converted by the gather warps): widths that
+    are / are not multiples of 8, un-warped input through the raw path, flow too wide for the raw box
+    (direct-gather fallback), md = 8 windows, output into a strided slice."""
+    B, C, H, W = shape
+    x1, x2, fl = rand_case(77 + W, B, C, H, W)
+    flow = None if flow_kind == "none" else (fl if flow_kind == "iid" else fl * 6.0)
+    t1, t2, tf = to_dev(x1, x2, flow)
+    h1, h2 = t1.to(dtype), t2.to(dtype)
+    for (p, md) in ((4, 4), (8, 8)):
+        ref = co.level_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), flow, p, 1, md, 1, 1, co.WARP_TORCH, 0.1)
+        for v in (1, 3):
+            out = ops.warp_corr_forward(h1, h2, tf, p, 1, md, 1, 1, 1, 0, 0.1, variant=v)
+            assert rel_err(out.float().cpu().numpy(), ref) < tol
+        D2 = (2 * md + 1) ** 2
+        cat = torch.zeros(B, D2 + 8, H, W, device=h1.device, dtype=dtype)
+        ops.warp_corr_forward(h1, h2, tf, p, 1, md, 1, 1, 1, 0, 0.1, out=cat[:, :D2])
+        assert rel_err(cat[:, :D2].float().cpu().numpy(), ref) < tol and torch.all(cat[:, D2:] == 0)
 
 
 def test_output_into_concat_buffer_and_strided_inputs():
