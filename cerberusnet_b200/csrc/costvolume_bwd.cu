@@ -46,6 +46,7 @@ struct BwdArgs {
   void* gdst[2];           // contiguous NCHW gradients: [0] wrt x1, [1] wrt the second correlation input
   int off;                 // md - pad
   int tiles_x, tiles_y;
+  int nwin;                // 9 x 9 displacement windows per axis (1 for max_displacement 4)
   int async_ok[2];         // fp32 and 16-byte alignment of s[] rows: stage the halo tiles with cp.async
 };
 
@@ -99,6 +100,18 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
   const bool mask = g.has_act && outp != nullptr;
   constexpr bool kF32 = std::is_same<T, float>::value;
 
+  // max_displacement > 4: the D x D displacement range is covered by 9 x 9 windows (origins 0, 8, ...,
+  // D - 9, as in the forward); the windows' contributions are accumulated into the output, rows /
+  // columns that an earlier window already covered are zeroed in G.
+  const int nwin = a.nwin;
+  for (int win = 0; win < nwin * nwin; ++win) {
+  const int wyi = win / nwin, wxi = win - wyi * nwin;
+  const int woy = min(8 * wyi, g.D - kDb), wox = min(8 * wxi, g.D - kDb);
+  const int lo_y = wyi == 0 ? 0 : min(8 * (wyi - 1), g.D - kDb) + kDb - woy;
+  const int lo_x = wxi == 0 ? 0 : min(8 * (wxi - 1), g.D - kDb) + kDb - wox;
+  const int ey0 = woy - g.md, ex0 = wox - g.md;   // pixel displacement of window entry (0, 0)
+  if (win > 0) __syncthreads();                    // previous window's write-out has finished with the S buffer
+
   BWD_TRACE(WHICH * 32 + 0);
   // ---- G tile: thread = pixel of the tile
   {
@@ -108,35 +121,38 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
     if constexpr (kF32) {
       const uint32_t gs_u32 = smem_u32(Gs) + 4u * (uint32_t)tid, os_u32 = smem_u32(Ss) + 4u * (uint32_t)tid;
       if (WHICH == 0) {
-        // the same output pixel in every displacement plane: one bounds test, one running offset
+        // the same output pixel in every displacement plane: one bounds test
         const int oy = qy - a.off, ox = qx - a.off;
         const bool ok = q_ok && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
-        const uint32_t nb = ok ? 4u : 0u;
         const long long o0 = (long long)min(max(oy, 0), g.outH - 1) * g.os[2] + min(max(ox, 0), g.outW - 1);
-        const T* gp = gout + o0;
-        const T* op = mask ? outp + o0 : nullptr;
-#pragma unroll 9
-        for (int plane = 0; plane < kD2b; ++plane) {
-          cp_async4(gs_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), gp, nb);
-          if (mask) { cp_async4(os_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), op, nb); op += g.os[1]; }
-          gp += g.os[1];
+#pragma unroll 1
+        for (int dyi = 0; dyi < kDb; ++dyi) {
+          const long long orow = o0 + (long long)((woy + dyi) * g.D + wox) * g.os[1];
+          const bool rok = ok && dyi >= lo_y;
+#pragma unroll
+          for (int dxi = 0; dxi < kDb; ++dxi) {
+            const int plane = dyi * kDb + dxi;
+            const uint32_t nb = (rok && dxi >= lo_x) ? 4u : 0u;
+            cp_async4(gs_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), gout + orow + (long long)dxi * g.os[1], nb);
+            if (mask) cp_async4(os_u32 + 4u * (uint32_t)(plane * (BT_Y * BT_X)), outp + orow + (long long)dxi * g.os[1], nb);
+          }
         }
       } else {
-        // plane (dyi, dxi) reads displacement plane 80 - plane at pixel q + (dyi - 4, dxi - 4):
-        // validity per row / column displacement as bit masks, offsets built incrementally
+        // window entry (dyi, dxi) = pixel displacement e reads the plane of -e at pixel q + e:
+        // validity per row / column displacement as bit masks
         unsigned row_ok = 0, col_ok = 0;
 #pragma unroll
         for (int d = 0; d < kDb; ++d) {
-          const int py = qy + d - kMDb, px = qx + d - kMDb;
-          if (q_ok && py >= 0 && py < g.H && py - a.off >= 0 && py - a.off < g.outH) row_ok |= 1u << d;
-          if (px >= 0 && px < g.W && px - a.off >= 0 && px - a.off < g.outW) col_ok |= 1u << d;
+          const int py = qy + ey0 + d, px = qx + ex0 + d;
+          if (q_ok && d >= lo_y && py >= 0 && py < g.H && py - a.off >= 0 && py - a.off < g.outH) row_ok |= 1u << d;
+          if (d >= lo_x && px >= 0 && px < g.W && px - a.off >= 0 && px - a.off < g.outW) col_ok |= 1u << d;
         }
-        const int oxc0 = qx - kMDb - a.off;
+        const int oxc0 = qx + ex0 - a.off;
 #pragma unroll 1
         for (int dyi = 0; dyi < kDb; ++dyi) {
-          const int oy = min(max(qy + dyi - kMDb - a.off, 0), g.outH - 1);
+          const int oy = min(max(qy + ey0 + dyi - a.off, 0), g.outH - 1);
           const bool rok = (row_ok >> dyi) & 1u;
-          const long long orow = (long long)(kD2b - 1 - dyi * kDb) * g.os[1] + (long long)oy * g.os[2];
+          const long long orow = (long long)((g.D - 1 - (woy + dyi)) * g.D + (g.D - 1 - wox)) * g.os[1] + (long long)oy * g.os[2];
 #pragma unroll
           for (int dxi = 0; dxi < kDb; ++dxi) {
             const int plane = dyi * kDb + dxi;
@@ -168,9 +184,9 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
 #pragma unroll
         for (int r = 0; r < 3 * kDb; ++r) {
           const int dyi = dy0 + r / kDb, dxi = r % kDb;
-          const int plane = dyi * kDb + dxi;
-          const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
-          const int d = (WHICH == 0) ? plane : (kD2b - 1 - plane);
+          const int py = (WHICH == 0) ? qy : qy + ey0 + dyi, px = (WHICH == 0) ? qx : qx + ex0 + dxi;
+          const int dg = (woy + dyi) * g.D + wox + dxi;
+          const int d = (WHICH == 0) ? dg : (g.D2 - 1 - dg);
           const int oy = min(max(py - a.off, 0), g.outH - 1), ox = min(max(px - a.off, 0), g.outW - 1);
           const long long o = (long long)d * g.os[1] + (long long)oy * g.os[2] + ox;
           gvv[r] = ldcg_f32(gout + o);
@@ -179,9 +195,9 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
 #pragma unroll
         for (int r = 0; r < 3 * kDb; ++r) {
           const int dyi = dy0 + r / kDb, dxi = r % kDb;
-          const int py = (WHICH == 0) ? qy : qy + dyi - kMDb, px = (WHICH == 0) ? qx : qx + dxi - kMDb;
+          const int py = (WHICH == 0) ? qy : qy + ey0 + dyi, px = (WHICH == 0) ? qx : qx + ex0 + dxi;
           const int oy = py - a.off, ox = px - a.off;
-          const bool ok = q_ok && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
+          const bool ok = q_ok && dyi >= lo_y && dxi >= lo_x && py >= 0 && py < g.H && px >= 0 && px < g.W && oy >= 0 && oy < g.outH && ox >= 0 && ox < g.outW;
           float v = ok ? gvv[r] : 0.f;
           if (!(ovv[r] > 0.f)) v *= g.slope;   // ovv == 1 when there is no activation
           Gs[(dy0 * kDb + r) * (BT_Y * BT_X) + tid] = v;
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
       const uint32_t ss_u32 = smem_u32(Ss);
       while (c < cmax) {
         const int hy = r / V4_ROW, v = r - hy * V4_ROW;
-        const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + 4 * v;
+        const int qy = iy0 + ey0 + hy, qx = ix0 + ex0 + 4 * v;
         const bool row_ok = qy >= 0 && qy < g.H && qx >= 0 && qx < g.W;
         const int nbytes = row_ok ? min(16, 4 * (g.W - qx)) : 0;
         const T* p = src + (long long)(c0 + c) * src_cs + (long long)(row_ok ? qy : 0) * src_hs + (row_ok ? qx : 0);
@@ -236,7 +252,7 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
           const int u = min(u0 + k * NT, total - 1);
           const int c = u / NPOS, i = u - c * NPOS;
           const int hy = i / BH_X, hx = i - hy * BH_X;
-          const int qy = min(max(iy0 - kMDb + hy, 0), g.H - 1), qx = min(max(ix0 - kMDb + hx, 0), g.W - 1);
+          const int qy = min(max(iy0 + ey0 + hy, 0), g.H - 1), qx = min(max(ix0 + ex0 + hx, 0), g.W - 1);
           tv[k] = ldg_f32(src + (long long)(c0 + c) * src_cs + (long long)qy * src_hs + qx);
         }
 #pragma unroll
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
           if (u < total) {
             const int c = u / NPOS, i = u - c * NPOS;
             const int hy = i / BH_X, hx = i - hy * BH_X;
-            const int qy = iy0 - kMDb + hy, qx = ix0 - kMDb + hx;
+            const int qy = iy0 + ey0 + hy, qx = ix0 + ex0 + hx;
             Ss[c * BS_CH + hy * BS_XS + hx] = (qy >= 0 && qy < g.H && qx >= 0 && qx < g.W) ? tv[k] : 0.f;
           }
         }
@@ -306,10 +322,17 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
     if (wpix_ok) {
       const float* orow = Os + wty * BT_X + wtx;
       T* gp = gdst + (long long)c0 * plane_elems + (long long)wy * g.W + wx;
+      if (win == 0) {
 #pragma unroll 8
-      for (int c = 0; c < cmax; ++c) gp[(long long)c * plane_elems] = from_f32<T>(orow[c * BO_CH]);
+        for (int c = 0; c < cmax; ++c) gp[(long long)c * plane_elems] = from_f32<T>(orow[c * BO_CH]);
+      } else {   // later displacement windows add to what this thread wrote before
+#pragma unroll 8
+        for (int c = 0; c < cmax; ++c)
+          gp[(long long)c * plane_elems] = from_f32<T>(to_f32<T>(gp[(long long)c * plane_elems]) + orow[c * BO_CH]);
+      }
     }
   }
+  }  // displacement windows
   BWD_TRACE(WHICH * 32 + 5);
 }
 
@@ -518,7 +541,7 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
                                 const void* gout, void* gx1, void* gx2, float* gflow, void* workspace,
                                 cudaStream_t stream) {
   const long long in_elems = (long long)g.B * g.C * g.H * g.W;
-  const bool fast = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == kMDb;
+  const bool fast = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= kMDb;
   cudaError_t e;
   if (fast) {
     // with a flow: the workspace holds the warped map and the gradient wrt it (2 * in_elems of T)
@@ -542,9 +565,10 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     a.gdst[0] = gx1;
     a.gdst[1] = flow ? (void*)gwarped : gx2;
     a.off = g.md - g.pad;
-    for (int w = 0; w < 2; ++w)
+    a.nwin = (g.D - kDb + 7) / 8 + 1;
+    for (int w = 0; w < 2; ++w)   // halo rows start at ix0 + window origin - md: 16-byte aligned only if md % 4 == 0
       a.async_ok[w] = std::is_same<T, float>::value && ((uintptr_t)a.s[w] % 16) == 0 && (a.s_ns[w] % 4) == 0 &&
-                      (a.s_cs[w] % 4) == 0 && (a.s_hs[w] % 4) == 0;
+                      (a.s_cs[w] % 4) == 0 && (a.s_hs[w] % 4) == 0 && (g.md % 4) == 0;
     a.tiles_x = (g.W + BT_X - 1) / BT_X;
     static const int force_ty = getenv("CERB_DEBUG_BWD_TY") ? atoi(getenv("CERB_DEBUG_BWD_TY")) : 0;
     const bool ty4 = force_ty ? force_ty == 4 : true;

@@ -161,6 +161,32 @@ def test_large_displacement_windows_vs_oracle(p, md, variant, with_flow):
     assert rel_err(out.cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("p,md", [(8, 8), (4, 10), (5, 5), (12, 12), (4, 8)])
+@pytest.mark.parametrize("with_flow", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_large_displacement_backward_vs_oracle(p, md, with_flow, dtype):
+    """Backward for max_displacement > 4 on the tiled kernel: contributions of the 9 x 9 displacement
+    windows are accumulated, overlapping rows / columns counted once."""
+    x1, x2, fl = rand_case(41 + md, 2, 10, 22, 40)
+    flow = fl if with_flow else None
+    t1, t2, tf = to_dev(x1, x2, flow)
+    t1, t2 = t1.to(dtype), t2.to(dtype)
+    x1, x2 = t1.float().cpu().numpy(), t2.float().cpu().numpy()
+    fwd = co.level_forward(x1, x2, flow, p, 1, md, 1, 1, co.WARP_TORCH, 0.1)
+    g = np.random.RandomState(6).standard_normal(fwd.shape).astype(np.float32)
+    tg = to_dev(g)[0].to(dtype)
+    g = tg.float().cpu().numpy()
+    out = ops.warp_corr_forward(t1, t2, tf, p, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    # the oracle masks with its own forward; use ours so both see the same LeakyReLU sign pattern
+    r1, r2, rf = co.level_backward(x1, x2, flow, g, p, 1, md, 1, 1, co.WARP_TORCH, 0.1)
+    g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, tg, p, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    tol = TOL if dtype == torch.float32 else 3e-2
+    assert rel_err(g1.float().cpu().numpy(), r1) < tol
+    assert rel_err(g2.float().cpu().numpy(), r2) < tol
+    if with_flow:
+        assert rel_err(gf.cpu().numpy(), rf) < tol
+
+
 def test_flow_far_outside_every_border():
     """Samples clipped at all four borders (stress set of SURVEY.md 8d: |flow| up to 3*md and
     beyond): border clamp identical to ATen clip_coordinates, zero flow-gradient where clipped."""

@@ -35,3 +35,10 @@ for (C, H, W) in ((32, 96, 320), (48, 96, 312)):
         fl8 = 2 * B * H * W * C * 289
         by8 = B * H * W * 4 * (2 * C + 289 + 2)
         print(f"md=8 B={B} C={C} {H}x{W}: windowed fast path {t8:9.1f} us ({fl8 / t8 / 1e6:5.2f} TFLOP/s, {by8 / t8 / 1e3:6.0f} GB/s)   generic kernel {tg:9.1f} us")
+# backward at md = 8 (tiled kernel, 4 displacement windows)
+for (B, C, H, W) in ((4, 32, 96, 320),):
+    x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
+    fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+    out = ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, 0, 0.1); gg = torch.randn_like(out)
+    tb = timeit(lambda: ops.warp_corr_backward(x1, x2, fl, out, gg, 8, 1, 8, 1, 1, 1, 0, 0.1), reps=5)
+    print(f"md=8 backward B={B} C={C} {H}x{W}: {tb:9.1f} us ({4 * B * H * W * C * 289 / tb / 1e6:5.2f} TFLOP/s)")
