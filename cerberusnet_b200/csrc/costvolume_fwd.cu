@@ -112,7 +112,11 @@ struct FwdCfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-// (y, dy) enumeration per strip: aligned lane pairs share the x2 row r = y + dy wherever possible.
+// (y, dy) enumeration per strip.  Lane pairs (2j, g+1), (2j+1, g) read the same x2 row r = 2j + g + 1
+// (adjacent-lane duplicate LDS.128 addresses are merged), and 8 consecutive entries -- a quarter-warp,
+// the unit a 128-bit shared access is processed in -- hold 8 distinct y for TY = 8, so the x1 loads
+// and the epilogue's accumulator stores (chunk swizzle keyed on y) are bank-conflict free.  The last
+// group takes the unpaired entries (even y with dy = 0, odd y with dy = 8).
 template <int TY>
 struct ComboLut {
   unsigned char y[TY * kD];
@@ -121,20 +125,16 @@ struct ComboLut {
 template <int TY>
 constexpr ComboLut<TY> make_combo_lut() {
   ComboLut<TY> l{};
-  unsigned char ly[TY * kD] = {}, ld[TY * kD] = {};
-  int n = 0, nl = 0;
-  for (int r = 0; r < TY + 2 * kMD; ++r) {
-    const int y0 = r - 2 * kMD > 0 ? r - 2 * kMD : 0;
-    const int y1 = r < TY - 1 ? r : TY - 1;
-    const int cnt = y1 - y0 + 1;
-    int i = 0;
-    for (; i + 1 < cnt; i += 2) {
-      l.y[n] = (unsigned char)(y0 + i); l.d[n] = (unsigned char)(r - (y0 + i)); ++n;
-      l.y[n] = (unsigned char)(y0 + i + 1); l.d[n] = (unsigned char)(r - (y0 + i + 1)); ++n;
+  int n = 0;
+  for (int g = 0; g < kD - 1; ++g)
+    for (int j = 0; j < TY / 2; ++j) {
+      l.y[n] = (unsigned char)(2 * j); l.d[n] = (unsigned char)(g + 1); ++n;
+      l.y[n] = (unsigned char)(2 * j + 1); l.d[n] = (unsigned char)g; ++n;
     }
-    if (i < cnt) { ly[nl] = (unsigned char)(y0 + i); ld[nl] = (unsigned char)(r - (y0 + i)); ++nl; }
+  for (int j = 0; j < TY / 2; ++j) {
+    l.y[n] = (unsigned char)(2 * j); l.d[n] = 0; ++n;
+    l.y[n] = (unsigned char)(2 * j + 1); l.d[n] = (unsigned char)(kD - 1); ++n;
   }
-  for (int i = 0; i < nl; ++i) { l.y[n] = ly[i]; l.d[n] = ld[i]; ++n; }
   return l;
 }
 __constant__ ComboLut<8> c_lut8 = make_combo_lut<8>();
