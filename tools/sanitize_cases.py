@@ -7,12 +7,12 @@ import cerberusnet_b200 as cb
 from cerberusnet_b200 import ops
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-def run(B, C, H, W, flow, variant=0, pad=4, sigma=2.0):
-    x1 = torch.randn(B, C, H, W, device=dev); x2 = torch.randn(B, C, H, W, device=dev)
+def run(B, C, H, W, flow, variant=0, pad=4, sigma=2.0, md=4, dtype=torch.float32):
+    x1 = torch.randn(B, C, H, W, device=dev).to(dtype); x2 = torch.randn(B, C, H, W, device=dev).to(dtype)
     fl = torch.randn(B, 2, H, W, device=dev) * sigma if flow else None
-    out = ops.warp_corr_forward(x1, x2, fl, pad, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=variant)
+    out = ops.warp_corr_forward(x1, x2, fl, pad, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=variant)
     g = torch.randn_like(out)
-    ops.warp_corr_backward(x1, x2, fl, out, g, pad, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    ops.warp_corr_backward(x1, x2, fl, out, g, pad, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
     torch.cuda.synchronize()
 for flow in (False, True):
     run(1, 32, 128, 256, flow)            # 8x32 config, TMA everywhere (one tile per CTA)
@@ -22,6 +22,14 @@ for flow in (False, True):
     run(3, 7, 9, 50, flow)                # ragged: no TMA (W % 4 != 0)
     run(2, 12, 26, 28, flow, pad=2)       # pad != md: LDG staging of x1
 run(1, 16, 32, 64, True, sigma=20.0)      # raw box does not fit: direct-gather fallback
+for flow in (False, True):
+    run(1, 12, 24, 64, flow, md=8, pad=8)                 # displacement windows, forward and backward
+    run(1, 12, 26, 44, flow, md=10, variant=3)            # three windows per axis, pad != md, 4x16 kernel
+    for dt in (torch.float16, torch.bfloat16):
+        run(1, 32, 40, 64, flow, dtype=dt, variant=1)     # 16-bit TMA raw path, 8x32
+        run(1, 24, 16, 32, flow, dtype=dt)                # 16-bit, 4x16 with cluster split
+        run(2, 8, 19, 37, flow, dtype=dt)                 # 16-bit, no TMA (W % 8 != 0)
+run(1, 16, 32, 64, True, sigma=20.0, dtype=torch.bfloat16, variant=1)   # 16-bit raw box misfit
 x = torch.randn(1, 6, 12, 20, device=dev); f = torch.randn(1, 2, 12, 20, device=dev) * 3
 o = ops.flow_warp_forward(x, f); ops.flow_warp_backward(x, f, torch.randn_like(o))
 ops.warp_corr_forward(x, x, f, 3, 3, 4, 2, 2); torch.cuda.synchronize()
