@@ -165,8 +165,9 @@ size_t cerb_warp_corr_backward_workspace(const cerb_corr_params* p, int has_flow
   Geom g;
   if (build_geom(p, has_flow != 0, g) != CERB_OK) return 0;
   if (!has_flow) return 0;
-  // the warped second map and the gradient wrt it
-  return 2 * (size_t)g.B * g.C * g.H * g.W * dtype_size(p->dtype);
+  // the warped second map and the gradient wrt it; 16-bit dtypes add an fp32 accumulator for the warp's splat
+  const size_t n = (size_t)g.B * g.C * g.H * g.W, es = dtype_size(p->dtype);
+  return 2 * n * es + (es == 2 ? n * sizeof(float) : 0);
 }
 
 int cerb_warp_corr_backward(const cerb_corr_params* p, const void* x1, const void* x2, const float* flow,

@@ -48,6 +48,7 @@ struct BwdArgs {
   int tiles_x, tiles_y;
   int nwin;                // 9 x 9 displacement windows per axis (1 for max_displacement 4)
   int async_ok[2];         // fp32 and 16-byte alignment of s[] rows: stage the halo tiles with cp.async
+  int vec4_ok[2];          // 16-bit and 8-byte alignment of s[] rows: stage the halo tiles with 4-element loads
 };
 
 // Register-tiled backward of the correlation.  Both gradients have the form
@@ -242,6 +243,37 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
       }
       cp_async_commit();
       cp_async_wait_all();
+    } else if (sizeof(T) == 2 && a.vec4_ok[WHICH]) {
+      // 16-bit: 8-byte loads of 4 elements (a halo row is 10 of them), 15 in flight per thread, widened on the way in
+      constexpr int V_ROW = BH_X / 4;
+      constexpr int U = BH_Y * V_ROW;
+      constexpr int NB = 15;
+      const int total = cmax * U;
+      for (int u0 = tid; u0 < total; u0 += NT * NB) {
+        uint2 pk[NB];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int u = min(u0 + k * NT, total - 1);
+          const int c = u / U, r = u - c * U;
+          const int hy = r / V_ROW, v = r - hy * V_ROW;
+          const int qy = min(max(iy0 + ey0 + hy, 0), g.H - 1), qx = min(max(ix0 + ex0 + 4 * v, 0), g.W - 4);
+          pk[k] = __ldg(reinterpret_cast<const uint2*>(src + (long long)(c0 + c) * src_cs + (long long)qy * src_hs + qx));
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          const int u = u0 + k * NT;
+          if (u < total) {
+            const int c = u / U, r = u - c * U;
+            const int hy = r / V_ROW, v = r - hy * V_ROW;
+            const int qy = iy0 + ey0 + hy, qx = ix0 + ex0 + 4 * v;
+            const bool ok = qy >= 0 && qy < g.H && qx >= 0 && qx + 3 < g.W;   // W % 4 == 0: a group is all in or all out
+            const T* hv = reinterpret_cast<const T*>(&pk[k]);
+            const float4 w4 = ok ? make_float4(to_f32<T>(hv[0]), to_f32<T>(hv[1]), to_f32<T>(hv[2]), to_f32<T>(hv[3]))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(Ss + c * BS_CH + hy * BS_XS + 4 * v) = w4;
+          }
+        }
+      }
     } else {
       constexpr int NPOS = BH_Y * BH_X;
       const int total = cmax * NPOS;
@@ -450,11 +482,11 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict_
 
 // flow_warp backward: grad_image splatted with atomics (pre-zeroed, contiguous), grad_flow written
 // (contiguous); `img` and `flow` carry strides, `gout` is contiguous.
-template <typename T>
+template <typename T, typename GT>
 __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict__ img, long long in_ns, long long in_cs,
                                                             long long in_hs, const float* __restrict__ flow,
                                                             long long f_ns, long long f_cs, long long f_hs,
-                                                            const T* __restrict__ gout, T* __restrict__ gimg,
+                                                            const T* __restrict__ gout, GT* __restrict__ gimg,
                                                             float* __restrict__ gflow, int B, int C, int H, int W,
                                                             int mode) {
   const long long plane = (long long)H * W;
@@ -489,11 +521,11 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (c0 + k < C) {
-          T* gp = gimg + ((long long)n * C + c0 + k) * plane;
-          if (to.w[0] != 0.f) atomic_add_t<T>(gp + to.off[0], gv[k] * to.w[0]);
-          if (to.w[1] != 0.f) atomic_add_t<T>(gp + to.off[1], gv[k] * to.w[1]);
-          if (to.w[2] != 0.f) atomic_add_t<T>(gp + to.off[2], gv[k] * to.w[2]);
-          if (to.w[3] != 0.f) atomic_add_t<T>(gp + to.off[3], gv[k] * to.w[3]);
+          GT* gp = gimg + ((long long)n * C + c0 + k) * plane;
+          if (to.w[0] != 0.f) atomic_add_t<GT>(gp + to.off[0], gv[k] * to.w[0]);
+          if (to.w[1] != 0.f) atomic_add_t<GT>(gp + to.off[1], gv[k] * to.w[1]);
+          if (to.w[2] != 0.f) atomic_add_t<GT>(gp + to.off[2], gv[k] * to.w[2]);
+          if (to.w[3] != 0.f) atomic_add_t<GT>(gp + to.off[3], gv[k] * to.w[3]);
           const float v_nw = v[k][0];
           const float v_ne = bx1 ? v[k][1] : 0.f;
           const float v_sw = by1 ? v[k][2] : 0.f;
@@ -507,6 +539,13 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
     gf[0] = in_x ? gix * pos_scale(W, mode) : 0.f;
     gf[plane] = in_y ? giy * pos_scale(H, mode) : 0.f;
   }
+}
+
+// fp32 splat accumulator -> 16-bit gradient (the fused backward accumulates the warp's splat in fp32)
+template <typename T>
+__global__ void __launch_bounds__(256) cvt_from_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f32<T>(src[i]);
 }
 
 // ------------------------------------------------------------------ host launchers -------
@@ -569,19 +608,34 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     for (int w = 0; w < 2; ++w)   // halo rows start at ix0 + window origin - md: 16-byte aligned only if md % 4 == 0
       a.async_ok[w] = std::is_same<T, float>::value && ((uintptr_t)a.s[w] % 16) == 0 && (a.s_ns[w] % 4) == 0 &&
                       (a.s_cs[w] % 4) == 0 && (a.s_hs[w] % 4) == 0 && (g.md % 4) == 0;
+    for (int w = 0; w < 2; ++w)
+      a.vec4_ok[w] = sizeof(T) == 2 && ((uintptr_t)a.s[w] % 8) == 0 && (a.s_ns[w] % 4) == 0 && (a.s_cs[w] % 4) == 0 &&
+                     (a.s_hs[w] % 4) == 0 && (g.md % 4) == 0 && (g.W % 4) == 0;
     a.tiles_x = (g.W + BT_X - 1) / BT_X;
     static const int force_ty = getenv("CERB_DEBUG_BWD_TY") ? atoi(getenv("CERB_DEBUG_BWD_TY")) : 0;
     const bool ty4 = force_ty ? force_ty == 4 : true;
     e = ty4 ? launch_tiled_pair<T, 4>(a, g, stream) : launch_tiled_pair<T, 8>(a, g, stream);
     if (e != cudaSuccess) return e;
     if (flow != nullptr) {
-      e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
-      if (e != cudaSuccess) return e;
-      flow_warp_bwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-          (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
-          g.C, g.H, g.W, g.warp_mode);
+      if (sizeof(T) == 2) {
+        // 16-bit: splat into an fp32 accumulator (third workspace region), then narrow -- 16-bit
+        // atomics are several times slower and round at every add
+        float* acc32 = reinterpret_cast<float*>(gwarped + in_elems);
+        e = cudaMemsetAsync(acc32, 0, (size_t)in_elems * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+        flow_warp_bwd_kernel<T, float><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
+            (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, acc32, gflow, g.B,
+            g.C, g.H, g.W, g.warp_mode);
+        cvt_from_f32_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(acc32, (T*)gx2, in_elems);
+      } else {
+        e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
+        if (e != cudaSuccess) return e;
+        flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
+            (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
+            g.C, g.H, g.W, g.warp_mode);
+      }
     }
-    count_launches(flow != nullptr ? 5 : 2);
+    count_launches(flow != nullptr ? (sizeof(T) == 2 ? 6 : 5) : 2);
     return cudaGetLastError();
   }
   // generic parameters
@@ -602,7 +656,7 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
       (const T*)out, (T*)gx1, gwarped);
   e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
   if (e != cudaSuccess) return e;
-  flow_warp_bwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
+  flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
       (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B, g.C,
       g.H, g.W, g.warp_mode);
   count_launches(4);
@@ -646,7 +700,7 @@ static cudaError_t warp_bwd_t(const void* image, const float* flow, const void* 
   cudaError_t e = cudaMemsetAsync(gimage, 0, (size_t)B * C * H * W * sizeof(T), stream);
   if (e != cudaSuccess) return e;
   const long long cs = (long long)H * W;
-  flow_warp_bwd_kernel<T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
+  flow_warp_bwd_kernel<T, T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
       (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (const T*)gout, (T*)gimage,
       gflow, B, C, H, W, mode);
   count_launches(2);

@@ -107,7 +107,8 @@ CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const voi
                                             const float* flow, void* out, int variant, cerb_stream_t stream);
 
 /* Bytes of scratch cerb_warp_corr_backward needs: 0 without a flow; with a flow the re-materialised
- * warped map and the gradient with respect to it, 2*B*C*H*W elements of the tensor dtype. */
+ * warped map and the gradient with respect to it, 2*B*C*H*W elements of the tensor dtype (plus B*C*H*W
+ * floats for 16-bit dtypes: the warp's splat is accumulated in fp32). */
 CERB_API size_t cerb_warp_corr_backward_workspace(const cerb_corr_params* p, int has_flow);
 
 /* Backward of cerb_warp_corr_forward.

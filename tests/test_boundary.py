@@ -80,6 +80,7 @@ def test_argument_errors_are_codes_not_aborts():
     assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params()), 0) == 0
     assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params(k=3, pad=5)), 0) == 0
     assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params()), 1) == 2 * 8 * 16 * 32 * 4
+    assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params(dtype=2)), 1) == (2 * 2 + 4) * 8 * 16 * 32
     assert lib.cerb_warp_corr_backward_workspace(ctypes.byref(_params(k=3, pad=5)), 1) == 2 * 8 * 16 * 32 * 4
 
 
