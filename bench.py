@@ -42,7 +42,7 @@ FMA_PEAK_TFLOPS = 70.4  # measured on this pool with tools/microbench/pipes.cu (
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the finest-level kernel, from the
 # ncu --set full capture summarised in profiles/r01_ncu_fwd_finest_level.txt (reads = algorithmic
 # input bytes; the 10.6 MB of output is still dirty in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES_FINEST = 8923136
+NCU_TRAFFIC_BYTES_FINEST = 8930560
 
 
 def level_bytes(C, H, W, warped, B=1, e=4):
