@@ -7,20 +7,28 @@
 //   F.leaky_relu_(out, 0.1)       nnet_training/nnet_models/pwcnet_sfd.py:182
 //
 // Fast path (kernel_size=1, stride1=stride2=1, max_displacement>=4; 4 is every model in the reference):
-//   persistent, warp-specialised CTAs, one output tile of TY x TX pixels at a time.
-//   * 3 producer warps: x1 tile per channel chunk by TMA (cp.async.bulk.tensor, zero fill = the
-//     correlation padding) and the (TY+8) x (TX+8) halo tile of the *warped* x2 gathered
-//     bilinearly straight from global/L2 into shared memory -- the warped map never exists in HBM;
+//   persistent, warp-specialised CTAs (16 warps), one output tile of TY x TX pixels at a time.
+//   * 1 TMA warp (one elected lane): x1 tile per channel chunk (cp.async.bulk.tensor, zero fill = the
+//     correlation padding) and, per chunk, the raw x2 source box that covers every bilinear tap of
+//     the tile's (TY+8) x (TX+8) halo (or the halo tile itself when there is no flow);
+//   * 6 gather warps: flow -> sample positions -> taps and weights once per tile (registers), then
+//     per chunk 4 LDS per sample from the raw box, blend, STS into the warped halo tile -- the
+//     warped map never exists in HBM.  16-bit inputs arrive as 16-bit boxes and are widened here;
 //   * 9 consumer warps: thread = (8-pixel strip, row y, row displacement dy) holding 8 x 9
 //     accumulators; per channel 2 + 4 LDS.128 feed 72 FFMA.  Lane pairs are arranged to read the
 //     same x2 row (B200 merges adjacent-lane duplicate LDS.128 addresses: 2.4 instead of 4
 //     clk/instr, tools/microbench/pipes.cu);
 //   * epilogue: divide by C, LeakyReLU, stage the 81 x TY x TX tile in shared memory (128B
-//     swizzle) and write it with one TMA store.
+//     swizzle), TMA store through a 5-D tensor map (x, y, dx, dy, n): one box for a CTA's last
+//     tile, nine per-column boxes issued as they are written otherwise;
+//   * few tiles (coarse pyramid levels): 4 x 16 tiles, channels split over KS consumer groups and
+//     over the CTAs of a thread-block cluster, partial tiles pushed through distributed shared
+//     memory and summed behind one hardware cluster barrier;
 //   * max_displacement > 4: the D x D displacement range is covered by 9 x 9 windows (origins 0, 8,
 //     ..., D-9; neighbours overlap by one row/column and write identical values there); a work unit
-//     is (tile, window), the halo tile origin shifts with the window and the output goes out
-//     through a 5-D tensor map (x, y, dx, dy, n).
+//     is (tile, window), the halo tile origin shifts with the window;
+//   * programmatic dependent launch: setup runs before griddepcontrol.wait, every role triggers
+//     launch_dependents after its last tile.
 // Generic path (any pad/kernel/stride parameters): one thread per output element.
 #include <cuda.h>
 
