@@ -6,8 +6,8 @@ the LeakyReLU(0.1) that follows it, behind the reference's own Python surfaces
 (``include/cerberus_costvolume.h``) shaped for the TensorRT correlation plugin's ``enqueue``.
 """
 from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, lib  # noqa: F401
-from .correlation import (Correlation, CorrelationFunction, CorrelationTorch, WarpCorrelation,  # noqa: F401
-                          WarpCorrelationFunction, warp_correlation)
+from .correlation import (Correlation, CorrelationFunction, CorrelationTorch, UpflowWarpCorrelationFunction,  # noqa: F401
+                          WarpCorrelation, WarpCorrelationFunction, warp_correlation, warp_correlation_upflow)
 from .flow_warp import FlowWarpFunction, flow_warp, mesh_grid, norm_grid  # noqa: F401
 from .install import install, patch_flow_warp  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401

@@ -50,7 +50,8 @@ class TrtCorrFields(ctypes.Structure):
 
 EXPORTS = [
     "cerb_abi_version", "cerb_error_string", "cerb_corr_output_dims", "cerb_warp_corr_forward",
-    "cerb_warp_corr_forward_variant", "cerb_warp_corr_backward_workspace", "cerb_warp_corr_backward",
+    "cerb_warp_corr_forward_variant", "cerb_warp_corr_forward_upflow", "cerb_warp_corr_backward_workspace",
+    "cerb_warp_corr_backward",
     "cerb_flow_warp_forward", "cerb_flow_warp_backward", "cerb_warp_corr_forward_host_workspace",
     "cerb_warp_corr_forward_host", "cerb_launch_count",
     "cerb_trt_corr_default_fields", "cerb_trt_corr_serialization_size", "cerb_trt_corr_serialize",
@@ -81,6 +82,8 @@ def lib() -> ctypes.CDLL:
     L.cerb_error_string.argtypes = [ctypes.c_int]
     L.cerb_corr_output_dims.argtypes = [pp] + [ctypes.POINTER(i32)] * 3
     L.cerb_warp_corr_forward.argtypes = [pp, vp, vp, f32p, vp, vp]
+    i64x4 = ctypes.POINTER(ctypes.c_int64)
+    L.cerb_warp_corr_forward_upflow.argtypes = [pp, vp, vp, f32p, i64x4, f32p, i64x4, vp, vp]
     L.cerb_warp_corr_forward_variant.argtypes = [pp, vp, vp, f32p, vp, ctypes.c_int, vp]
     L.cerb_warp_corr_backward_workspace.argtypes = [pp, ctypes.c_int]
     L.cerb_warp_corr_backward_workspace.restype = ctypes.c_size_t

@@ -173,6 +173,53 @@ def warp_correlation(input1: torch.Tensor, input2: torch.Tensor, flow: Optional[
                                  corr_multiply, warp_mode, leaky_slope)
 
 
+class UpflowWarpCorrelationFunction(torch.autograd.Function):
+    """(out, flow_up) with flow_up = interpolate(2 * flow_coarse, x2, bilinear, align_corners=True) and
+    out = leaky_relu(correlation(x1, flow_warp(x2, flow_up)), slope): the decoder's four steps
+    (pwcnet_sfd.py:176-182) in one launch.  Backward: the fused backward gives the gradient with respect
+    to flow_up; the up-sampling's adjoint (ATen) carries it, plus whatever arrives on flow_up, to flow_coarse."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, input1, input2, flow_coarse, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1,
+                corr_multiply=1, warp_mode=WARP_TORCH, leaky_slope=0.1):
+        out, flow_up = ops.warp_corr_forward_upflow(input1, input2, flow_coarse, pad_size, kernel_size, max_displacement,
+                                                    stride1, stride2, corr_multiply, warp_mode, leaky_slope)
+        ctx.cfg = (pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply, warp_mode, leaky_slope)
+        ctx.coarse_shape = tuple(flow_coarse.shape)
+        ctx.coarse_dtype = flow_coarse.dtype
+        ctx.save_for_backward(input1, input2, flow_up, out)
+        return out, flow_up
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_out, grad_flow_up):
+        input1, input2, flow_up, out = ctx.saved_tensors
+        pad, k, md, s1, s2, mult, mode, slope = ctx.cfg
+        g1, g2, gflow = ops.warp_corr_backward(input1, input2, flow_up, out if slope is not None else None,
+                                               grad_out.contiguous(), pad, k, md, s1, s2, mult, mode, slope)
+        if grad_flow_up is not None:
+            gflow = gflow + grad_flow_up.float()
+        H, W = flow_up.shape[-2:]
+        gcoarse = torch.ops.aten.upsample_bilinear2d_backward(gflow.contiguous(), [H, W], list(ctx.coarse_shape), True,
+                                                              2.0, 2.0) * 2
+        return g1, g2, gcoarse.to(ctx.coarse_dtype), None, None, None, None, None, None, None, None
+
+
+def warp_correlation_upflow(input1: torch.Tensor, input2: torch.Tensor, flow_coarse: torch.Tensor, pad_size: int = 4,
+                            kernel_size: int = 1, max_displacement: int = 4, stride1: int = 1, stride2: int = 1,
+                            corr_multiply: int = 1, warp_mode: int = WARP_TORCH, leaky_slope: Optional[float] = 0.1,
+                            out: Optional[torch.Tensor] = None, flow_up: Optional[torch.Tensor] = None):
+    """``(cost_volume, flow_up)`` from the next-coarser level's flow.  ``out`` / ``flow_up``
+    (e.g. slices of the decoder's concat buffer) are honoured on the no-grad path."""
+    needs_grad = torch.is_grad_enabled() and any(t.requires_grad for t in (input1, input2, flow_coarse))
+    if needs_grad:
+        return UpflowWarpCorrelationFunction.apply(input1, input2, flow_coarse, pad_size, kernel_size, max_displacement,
+                                                   stride1, stride2, corr_multiply, warp_mode, leaky_slope)
+    return ops.warp_corr_forward_upflow(input1, input2, flow_coarse, pad_size, kernel_size, max_displacement, stride1,
+                                        stride2, corr_multiply, warp_mode, leaky_slope, out=out, flow_up=flow_up)
+
+
 class WarpCorrelation(Correlation):
     """``Correlation`` with the decoder's surrounding ops fused in.
 

@@ -156,6 +156,28 @@ CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const voi
   return (int)e;
 }
 
+int cerb_warp_corr_forward_upflow(const cerb_corr_params* p, const void* x1, const void* x2, const float* flow_coarse,
+                                  const int64_t coarse_stride[4], float* flow_up, const int64_t up_stride[4], void* out,
+                                  cerb_stream_t stream) {
+  Geom g;
+  const int rc = build_geom(p, true, g);
+  if (rc != CERB_OK) return rc;
+  if (!x1 || !x2 || !out || !flow_coarse || !flow_up) return CERB_EINVAL;
+  if ((g.H & 1) || (g.W & 1) || g.H < 4 || g.W < 4) return CERB_EINVAL;   // scale_factor = 2 exactly, coarse maps at least 2x2
+  if (!is_fast(g) || g.pad != g.md) return CERB_EUNSUPPORTED;             // tiles must cover the whole image
+  UpFlow uf;
+  uf.coarse = flow_coarse; uf.up = flow_up; uf.Hc = g.H / 2; uf.Wc = g.W / 2;
+  bool ok1, ok2;
+  static const int64_t contiguous[4] = {0, 0, 0, 0};
+  fill_strides(coarse_stride ? coarse_stride : contiguous, uf.cs, 2, uf.Hc, uf.Wc, ok1);
+  fill_strides(up_stride ? up_stride : contiguous, uf.us, 2, g.H, g.W, ok2);
+  if (!(ok1 && ok2)) return CERB_ESTRIDE;
+  const cudaError_t e = launch_warp_corr_forward(g, p->dtype, x1, x2, nullptr, out, CERB_FWD_VARIANT_AUTO,
+                                                 (cudaStream_t)stream, &uf);
+  if (e == cudaSuccess) count_launches(1);
+  return (int)e;
+}
+
 int cerb_warp_corr_forward(const cerb_corr_params* p, const void* x1, const void* x2, const float* flow, void* out,
                            cerb_stream_t stream) {
   return cerb_warp_corr_forward_variant(p, x1, x2, flow, out, CERB_FWD_VARIANT_AUTO, stream);

@@ -168,6 +168,13 @@ struct FwdArgs {
   int use_tma_out;  // output tile by TMA store
   int raw16;        // 16-bit inputs: raw x2 box and x1 tile by TMA as 16-bit data, converted by the gather warps
   int out_vec8;     // 16-bit output: 16-byte stores straight from the staged tile
+  // fused flow up-sampling: coarse flow in, up-sampled flow out (cflow == nullptr: off)
+  const float* cflow;
+  long long cfs[3];
+  int Hc, Wc;
+  float up_sy, up_sx;   // ATen's align_corners=True scale (in - 1) / (out - 1), fp32
+  float* flow_up;
+  long long fus[3];
   int csplit_log2;
   int csplit;       // CTAs per cluster sharing one tile, each taking a slice of the channel chunks (1 = off)
   int dbg_iter;
@@ -283,7 +290,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const int pt = tid - Cfg::NCONS;
     const int pwarp = pt >> 5;
     const int lane = pt & 31;
-    const bool warped = a.flow != nullptr;
+    const bool warped = a.flow != nullptr || a.cflow != nullptr;
     const bool raw16 = sizeof(T) == 2 && a.raw16;           // 16-bit inputs staged through the raw stage
     const bool reduce_bbox = (warped || raw16) && a.use_tma_raw;
     int red_par = 0;
@@ -423,7 +430,56 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         // unconditional loads from clamped (always valid) addresses -- loads left inside the
         // validity branches are issued one round trip at a time
         float fu[Cfg::POS_PER_THREAD], fv[Cfg::POS_PER_THREAD];
-        if (warped) {
+        if (a.cflow != nullptr) {
+          // flow = interpolate(2 * coarse, scale_factor=2, bilinear, align_corners=True), evaluated per halo
+          // position with ATen's arithmetic (upsample_bilinear2d: src = scale * dst, lambda = src - int(src));
+          // doubling commutes exactly with the blend.  Tile-interior positions also write the result out.
+          const float* cn = a.cflow + (long long)n * a.cfs[0];
+          float cv[Cfg::POS_PER_THREAD][8], lam[Cfg::POS_PER_THREAD][2];
+#pragma unroll
+          for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+            const int i = gt + j * kGatherThreads;
+            const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
+            const int cy = min(max(qy0 + hy, 0), g.H - 1), cx = min(max(qx0 + hx, 0), g.W - 1);
+            const float h1r = __fmul_rn(a.up_sy, (float)cy), w1r = __fmul_rn(a.up_sx, (float)cx);
+            const int h1 = (int)h1r, w1 = (int)w1r;
+            const int h1p = (h1 < a.Hc - 1) ? 1 : 0, w1p = (w1 < a.Wc - 1) ? 1 : 0;
+            lam[j][0] = __fsub_rn(h1r, (float)h1);
+            lam[j][1] = __fsub_rn(w1r, (float)w1);
+            const float* p0 = cn + (long long)h1 * a.cfs[2] + w1;
+            const float* p1 = p0 + (long long)h1p * a.cfs[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              cv[j][4 * c + 0] = __ldg(p0 + c * a.cfs[1]);
+              cv[j][4 * c + 1] = __ldg(p0 + c * a.cfs[1] + w1p);
+              cv[j][4 * c + 2] = __ldg(p1 + c * a.cfs[1]);
+              cv[j][4 * c + 3] = __ldg(p1 + c * a.cfs[1] + w1p);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+            const float h1l = lam[j][0], w1l = lam[j][1];
+            const float h0l = __fsub_rn(1.f, h1l), w0l = __fsub_rn(1.f, w1l);
+            float r[2];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              // h0l * (w0l * v00 + w1l * v01) + h1l * (w0l * v10 + w1l * v11) as nvcc contracts it in ATen
+              const float t0 = __fmaf_rn(w0l, cv[j][4 * c + 0], __fmul_rn(w1l, cv[j][4 * c + 1]));
+              const float t1 = __fmaf_rn(w0l, cv[j][4 * c + 2], __fmul_rn(w1l, cv[j][4 * c + 3]));
+              r[c] = __fmul_rn(2.f, __fmaf_rn(h0l, t0, __fmul_rn(h1l, t1)));
+            }
+            fu[j] = r[0];
+            fv[j] = r[1];
+            const int i = gt + j * kGatherThreads;
+            const int hy = i / Cfg::HX, hx = i - hy * Cfg::HX;
+            const int qy = qy0 + hy, qx = qx0 + hx;
+            if (i < Cfg::NPOS && qy >= iy0 && qy < iy0 + TY && qx >= ix0 && qx < ix0 + TX && qy < g.H && qx < g.W) {
+              float* up = a.flow_up + (long long)n * a.fus[0] + (long long)qy * a.fus[2] + qx;
+              up[0] = r[0];
+              up[a.fus[1]] = r[1];
+            }
+          }
+        } else if (warped) {
           const float* fn = a.flow + (long long)n * g.fls[0];
 #pragma unroll
           for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
@@ -1016,11 +1072,21 @@ static int num_sms() {
 
 template <typename T, int TY, int TX, int KS, int CC, int RS>
 static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
-                               int force_no_tma, bool allow_csplit, cudaStream_t stream) {
+                               int force_no_tma, bool allow_csplit, cudaStream_t stream, const UpFlow* uf) {
   using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
   FwdArgs a;
   a.g = g;
   a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out;
+  a.cflow = nullptr; a.flow_up = nullptr; a.Hc = a.Wc = 0; a.up_sy = a.up_sx = 0.f;
+  for (int i = 0; i < 3; ++i) a.cfs[i] = a.fus[i] = 0;
+  if (uf != nullptr) {
+    a.cflow = uf->coarse; a.flow_up = uf->up; a.Hc = uf->Hc; a.Wc = uf->Wc;
+    for (int i = 0; i < 3; ++i) { a.cfs[i] = uf->cs[i]; a.fus[i] = uf->us[i]; }
+    // ATen area_pixel_compute_scale<float>(in, out, align_corners=true): (float)(in - 1) / (out - 1)
+    a.up_sy = g.H > 1 ? (float)(uf->Hc - 1) / (float)(g.H - 1) : 0.f;
+    a.up_sx = g.W > 1 ? (float)(uf->Wc - 1) / (float)(g.W - 1) : 0.f;
+  }
+  const bool warped_in = flow != nullptr || uf != nullptr;
   a.off = g.md - g.pad;
   a.tiles_x = (g.outW + TX - 1) / TX;
   a.tiles_y = (g.outH + TY - 1) / TY;
@@ -1045,9 +1111,9 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
     if ((tma_mask & 1) && (a.off % 4) == 0)
       a.use_tma_in = make_tmap_f32(&tm_x1, x1, g.W, g.H, g.C, g.B, g.x1s, TX, TY, CC, TX == 32) ? 1 : 0;
     // (x2 halo tiles start at bx0 - pad + window origin; origins are multiples of 8 and D - 9 = 2 md - 8)
-    if ((tma_mask & 4) && (g.pad % 4) == 0 && (a.nwin == 1 || (g.md % 2) == 0) && flow == nullptr)
+    if ((tma_mask & 4) && (g.pad % 4) == 0 && (a.nwin == 1 || (g.md % 2) == 0) && !warped_in)
       a.use_tma_x2 = make_tmap_f32(&tm_x2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::XS, Cfg::HY, CC, false) ? 1 : 0;
-    if ((tma_mask & 8) && flow != nullptr)
+    if ((tma_mask & 8) && warped_in)
       a.use_tma_raw = make_tmap_f32(&tm_raw, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W, Cfg::RAW_H, CC, false) ? 1 : 0;
     if (tma_mask & 2)
       a.use_tma_out = (make_tmap_out5d(&tm_out, out, g, TX, TY, kD) &&
@@ -1115,7 +1181,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
 
 template <typename T>
 static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
-                                int variant, cudaStream_t stream) {
+                                int variant, cudaStream_t stream, const UpFlow* uf) {
   const bool fast_ok = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= kMD && variant != CERB_FWD_VARIANT_GENERIC;
   if (fast_ok) {
     const int no_tma = (variant == CERB_FWD_VARIANT_FAST_NOTMA || variant == CERB_FWD_VARIANT_SMALL_NOTMA) ? 1 : 0;
@@ -1126,9 +1192,10 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
       const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8) * nwin * nwin;
       small = big_tiles < (long long)num_sms() * 3 / 4;
     }
-    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, true, stream);
-    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, false, stream);
+    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, true, stream, uf);
+    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, false, stream, uf);
   }
+  if (uf != nullptr) return cudaErrorNotSupported;   // the generic kernel has no fused up-sampling
   const long long total = (long long)g.B * g.D2 * g.outH * g.outW;
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
@@ -1138,11 +1205,11 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
 }
 
 cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
-                                     void* out, int variant, cudaStream_t stream) {
+                                     void* out, int variant, cudaStream_t stream, const UpFlow* uf) {
   switch (dtype) {
-    case CERB_F32: return launch_fwd_t<float>(g, x1, x2, flow, out, variant, stream);
-    case CERB_F16: return launch_fwd_t<__half>(g, x1, x2, flow, out, variant, stream);
-    case CERB_BF16: return launch_fwd_t<__nv_bfloat16>(g, x1, x2, flow, out, variant, stream);
+    case CERB_F32: return launch_fwd_t<float>(g, x1, x2, flow, out, variant, stream, uf);
+    case CERB_F16: return launch_fwd_t<__half>(g, x1, x2, flow, out, variant, stream, uf);
+    case CERB_BF16: return launch_fwd_t<__nv_bfloat16>(g, x1, x2, flow, out, variant, stream, uf);
     default: return cudaErrorInvalidValue;
   }
 }

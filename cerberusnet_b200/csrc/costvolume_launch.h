@@ -18,8 +18,18 @@ enum {
 
 namespace cerb {
 
+// Fused flow up-sampling: the flow of the next-coarser level, (B,2,H/2,W/2), is doubled and
+// bilinearly up-sampled (align_corners=True) inside the warp prologue; the up-sampled flow is also written out.
+struct UpFlow {
+  const float* coarse;
+  long long cs[3];   // N, C, H strides of the coarse flow (elements)
+  int Hc, Wc;
+  float* up;         // (B,2,H,W) destination, may be a channel slice of a wider tensor
+  long long us[3];
+};
+
 cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
-                                     void* out, int variant, cudaStream_t stream);
+                                     void* out, int variant, cudaStream_t stream, const UpFlow* upflow = nullptr);
 
 // workspace: fp32 [B,C,H,W] accumulation buffer for grad_x2 when dtype is 16-bit and flow != NULL
 cudaError_t launch_warp_corr_backward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,

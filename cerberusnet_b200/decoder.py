@@ -21,7 +21,7 @@ import torch.nn.functional as F
 
 from . import ops
 from ._lib import WARP_TORCH
-from .correlation import warp_correlation
+from .correlation import warp_correlation, warp_correlation_upflow
 
 
 def _conv(cin: int, cout: int, k: int = 3, stride: int = 1, dilation: int = 1, act: bool = True) -> nn.Sequential:
@@ -52,8 +52,10 @@ class FlowDecoder(nn.Module):
     """Coarse-to-fine flow decoder over two feature pyramids (coarsest first)."""
 
     def __init__(self, channels_in: Sequence[int], max_displacement: int = 4, proj_channels: int = 32,
-                 output_level: int = 4, warp_mode: int = WARP_TORCH, leaky_slope: float = 0.1):
+                 output_level: int = 4, warp_mode: int = WARP_TORCH, leaky_slope: float = 0.1,
+                 fuse_upsample: bool = True):
         super().__init__()
+        self.fuse_upsample = fuse_upsample
         self.md, self.warp_mode, self.slope, self.output_level = max_displacement, warp_mode, leaky_slope, output_level
         self.n_corr = (2 * max_displacement + 1) ** 2
         # only the levels the loop visits get a projection: DDP requires every parameter to take part
@@ -79,19 +81,32 @@ class FlowDecoder(nn.Module):
         B, _, h, w = pyr1[0].shape
         flow = pyr1[0].new_zeros(B, 2, h, w)
         for level, (f1, f2) in enumerate(zip(pyr1, pyr2)):
-            if level > 0:
-                flow = F.interpolate(flow * 2, scale_factor=2, mode="bilinear", align_corners=True)
+            H, W = f1.shape[2:]
+            # flow = interpolate(2 * flow, x2, bilinear, align_corners=True) rides along in the op's prologue
+            #  whenever this level is exactly twice the previous one
+            fuse_up = level > 0 and self.fuse_upsample and H == 2 * flow.shape[2] and W == 2 * flow.shape[3]
+            if level > 0 and not fuse_up:
+                flow = F.interpolate(flow * 2, size=(H, W), mode="bilinear", align_corners=True)
             proj = self.proj[level](f1)
             warp_flow = flow if level > 0 else None
             if torch.is_grad_enabled():
-                cost = warp_correlation(f1, f2, warp_flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode, self.slope)
+                if fuse_up:
+                    cost, flow = warp_correlation_upflow(f1, f2, flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode,
+                                                         self.slope)
+                else:
+                    cost = warp_correlation(f1, f2, warp_flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode, self.slope)
                 x = torch.cat([cost, proj, flow], 1)
-            else:  # inference: the activated cost volume lands in the concat buffer directly
-                x = f1.new_empty(B, self.n_corr + proj.shape[1] + 2, f1.shape[2], f1.shape[3])
-                ops.warp_corr_forward(f1, f2, warp_flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode, self.slope,
-                                      out=x[:, :self.n_corr])
+            else:  # inference: the activated cost volume (and the up-sampled flow) land in the concat buffer directly
+                x = f1.new_empty(B, self.n_corr + proj.shape[1] + 2, H, W)
+                if fuse_up:
+                    ops.warp_corr_forward_upflow(f1, f2, flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode, self.slope,
+                                                 out=x[:, :self.n_corr], flow_up=x[:, -2:])
+                    flow = x[:, -2:]
+                else:
+                    ops.warp_corr_forward(f1, f2, warp_flow, self.md, 1, self.md, 1, 1, 1, self.warp_mode, self.slope,
+                                          out=x[:, :self.n_corr])
+                    x[:, -2:] = flow
                 x[:, self.n_corr:self.n_corr + proj.shape[1]] = proj
-                x[:, -2:] = flow
             feat, dflow = self._estimate(x)
             flow = flow + dflow
             flow = flow + self.context(torch.cat([feat, flow], 1))

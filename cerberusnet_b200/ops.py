@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, check, current_stream_ptr, lib, make_params,
                    output_dims, ptr, require_cuda)
 
-__all__ = ["warp_corr_forward", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
+__all__ = ["warp_corr_forward", "warp_corr_forward_upflow", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
            "WARP_TORCH", "WARP_TRT", "WARP_TORCH_CPU"]
 
 
@@ -68,6 +68,45 @@ def warp_corr_forward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.T
                                                   ctypes.c_void_p(current_stream_ptr(x1.device)))
     check(rc, "cerb_warp_corr_forward")
     return out
+
+
+def warp_corr_forward_upflow(x1: torch.Tensor, x2: torch.Tensor, flow_coarse: torch.Tensor, pad_size: int = 4,
+                             kernel_size: int = 1, max_displacement: int = 4, stride1: int = 1, stride2: int = 1,
+                             corr_multiply: int = 1, warp_mode: int = WARP_TORCH, leaky_slope: Optional[float] = None,
+                             out: Optional[torch.Tensor] = None, flow_up: Optional[torch.Tensor] = None):
+    """The decoder's ``flow = F.interpolate(flow_coarse * 2, scale_factor=2, mode='bilinear',
+    align_corners=True)`` (pwcnet_sfd.py:176) fused into :func:`warp_corr_forward`.
+
+    ``flow_coarse`` is (B,2,H/2,W/2); returns ``(out, flow_up)`` where ``flow_up`` (B,2,H,W) is the
+    up-sampled flow the decoder goes on to use -- pass a channel slice of the concat buffer to
+    have it written in place.  Needs pad_size == max_displacement >= 4, kernel_size 1, strides 1.
+    """
+    require_cuda(x1, x2, flow_coarse, out, flow_up)
+    if x1.shape != x2.shape or x1.dtype != x2.dtype:
+        raise CostVolumeError("inputs must have the same shape and dtype")
+    B, C, H, W = x1.shape
+    if flow_coarse.shape != (B, 2, H // 2, W // 2) or H % 2 or W % 2:
+        raise CostVolumeError(f"flow_coarse must be (B,2,H/2,W/2) with even H, W; got {tuple(flow_coarse.shape)}")
+    x1, x2 = _inner_contig(x1), _inner_contig(x2)
+    flow_coarse = _inner_contig(flow_coarse.float())
+    shape = corr_output_shape(x1.shape, pad_size, kernel_size, max_displacement, stride1, stride2)
+    if out is None:
+        out = torch.empty(shape, dtype=x1.dtype, device=x1.device)
+    elif tuple(out.shape) != shape or out.dtype != x1.dtype or out.stride(3) != 1:
+        raise CostVolumeError(f"out must be {shape} {x1.dtype} with unit W stride")
+    if flow_up is None:
+        flow_up = torch.empty(B, 2, H, W, dtype=torch.float32, device=x1.device)
+    elif tuple(flow_up.shape) != (B, 2, H, W) or flow_up.dtype != torch.float32 or flow_up.stride(3) != 1:
+        raise CostVolumeError("flow_up must be (B,2,H,W) float32 with unit W stride")
+    p = make_params(x1, x2, None, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
+                    warp_mode, leaky_slope)
+    cs = (ctypes.c_int64 * 4)(*flow_coarse.stride())
+    us = (ctypes.c_int64 * 4)(*flow_up.stride())
+    with torch.cuda.device(x1.device):
+        rc = lib().cerb_warp_corr_forward_upflow(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow_coarse), cs, ptr(flow_up), us,
+                                                 ptr(out), ctypes.c_void_p(current_stream_ptr(x1.device)))
+    check(rc, "cerb_warp_corr_forward_upflow")
+    return out, flow_up
 
 
 def warp_corr_backward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor],

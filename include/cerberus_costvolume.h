@@ -106,6 +106,16 @@ CERB_API int cerb_warp_corr_forward(const cerb_corr_params* p, const void* x1, c
 CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const void* x1, const void* x2,
                                             const float* flow, void* out, int variant, cerb_stream_t stream);
 
+/* Same forward with the decoder's flow up-sampling fused in (pwcnet_sfd.py:176):
+ *   flow = interpolate(2 * flow_coarse, scale_factor=2, mode='bilinear', align_corners=True)
+ * flow_coarse is (B,2,H/2,W/2) fp32 (H, W even), evaluated per sample with ATen's arithmetic; the up-sampled flow
+ * the decoder needs afterwards is written to flow_up (B,2,H,W) fp32 -- e.g. the last two channels of the concat
+ * buffer.  Strides as in cerb_corr_params (elements, all zero = contiguous).  Needs the fast kernels
+ * (kernel_size=1, strides 1, max_displacement >= 4) and pad_size == max_displacement, else CERB_EUNSUPPORTED. */
+CERB_API int cerb_warp_corr_forward_upflow(const cerb_corr_params* p, const void* x1, const void* x2,
+                                           const float* flow_coarse, const int64_t coarse_stride[4], float* flow_up,
+                                           const int64_t up_stride[4], void* out, cerb_stream_t stream);
+
 /* Bytes of scratch cerb_warp_corr_backward needs: 0 without a flow; with a flow the re-materialised
  * warped map and the gradient with respect to it, 2*B*C*H*W elements of the tensor dtype (plus B*C*H*W
  * floats for 16-bit dtypes: the warp's splat is accumulated in fp32). */

@@ -187,6 +187,76 @@ def test_large_displacement_backward_vs_oracle(p, md, with_flow, dtype):
         assert rel_err(gf.cpu().numpy(), rf) < tol
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 16, 32), (2, 20, 24, 64), (1, 16, 64, 128), (1, 8, 128, 256), (2, 12, 10, 36)])
+@pytest.mark.parametrize("md", [4, 8])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_flow_upsample_matches_interpolate(shape, md, dtype):
+    """SURVEY 8f-1 / pwcnet_sfd.py:176: flow = interpolate(2*flow_coarse, scale_factor=2, bilinear,
+    align_corners=True) fused into the warp prologue.  The up-sampled flow must equal ATen's on the
+    GPU bit for bit, the cost volume must equal the un-fused op fed with ATen's flow."""
+    B, C, H, W = shape
+    x1, x2, _ = rand_case(91 + H, B, C, H, W)
+    g = torch.Generator().manual_seed(7 + W)
+    coarse = (torch.randn(B, 2, H // 2, W // 2, generator=g) * 1.2).cuda()
+    t1, t2 = to_dev(x1, x2)
+    t1, t2 = t1.to(dtype), t2.to(dtype)
+    ref_flow = torch.nn.functional.interpolate(coarse * 2, scale_factor=2, mode="bilinear", align_corners=True)
+    ref_out = ops.warp_corr_forward(t1, t2, ref_flow, md, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    cat = torch.zeros(B, (2 * md + 1) ** 2 + 5 + 2, H, W, device=t1.device, dtype=torch.float32)
+    out, up = ops.warp_corr_forward_upflow(t1, t2, coarse, md, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1, flow_up=cat[:, -2:])
+    assert torch.equal(up, ref_flow), float((up - ref_flow).abs().max())
+    assert torch.equal(out, ref_out)
+    assert torch.all(cat[:, :-2] == 0)
+    # a strided coarse flow (channel slice of a wider tensor) and a freshly allocated flow_up
+    wide = torch.zeros(B, 4, H // 2, W // 2, device=t1.device)
+    wide[:, 1:3] = coarse
+    out2, up2 = ops.warp_corr_forward_upflow(t1, t2, wide[:, 1:3], md, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
+    assert torch.equal(up2, ref_flow) and torch.equal(out2, ref_out)
+
+
+def test_fused_flow_upsample_autograd_and_decoder():
+    """Gradients through the fused up-sampling equal those of the un-fused composition
+    (interpolate -> fused warp+corr), and the decoder harness gives the same flows either way."""
+    x1, x2, _ = rand_case(5, 2, 16, 16, 32)
+    t1, t2 = to_dev(x1, x2)
+    coarse = torch.randn(2, 2, 8, 16, device=t1.device) * 1.3
+    gout = torch.randn(2, 81, 16, 32, device=t1.device)
+    gup = torch.randn(2, 2, 16, 32, device=t1.device)
+    grads = []
+    for fused in (True, False):
+        a, b, c = (t.clone().requires_grad_() for t in (t1, t2, coarse))
+        if fused:
+            out, up = cb.warp_correlation_upflow(a, b, c)
+        else:
+            up = torch.nn.functional.interpolate(c * 2, scale_factor=2, mode="bilinear", align_corners=True)
+            out = cb.warp_correlation(a, b, up)
+        ((out * gout).sum() + (up * gup).sum()).backward()
+        grads.append((out.detach(), up.detach(), a.grad, b.grad, c.grad))
+    for u, v in zip(*grads):
+        assert rel_err(u.cpu().numpy(), v.cpu().numpy()) < 2e-6
+    from cerberusnet_b200.decoder import FlowNetLite
+    torch.manual_seed(1)
+    net = FlowNetLite().to(dev()).eval()
+    img1, img2 = torch.rand(1, 3, 128, 256, device=dev()), torch.rand(1, 3, 128, 256, device=dev())
+    with torch.no_grad():
+        f_fused = net(img1, img2)["flow"]
+        net.decoder.fuse_upsample = False
+        f_plain = net(img1, img2)["flow"]
+    for u, v in zip(f_fused, f_plain):
+        assert rel_err(u.cpu().numpy(), v.cpu().numpy()) < 1e-6
+
+
+def test_fused_flow_upsample_argument_checks():
+    x = torch.randn(1, 8, 16, 32, device="cuda")
+    c = torch.randn(1, 2, 8, 16, device="cuda")
+    with pytest.raises(cb.CostVolumeError):   # pad != max_displacement: tiles do not cover the image
+        ops.warp_corr_forward_upflow(x, x, c, 2, 1, 4, 1, 1)
+    with pytest.raises(cb.CostVolumeError):   # generic parameters have no fused path
+        ops.warp_corr_forward_upflow(x, x, c, 3, 3, 3, 1, 1)
+    with pytest.raises(cb.CostVolumeError):
+        ops.warp_corr_forward_upflow(x, x, c[:, :, :4], 4, 1, 4, 1, 1)
+
+
 def test_flow_far_outside_every_border():
     """Samples clipped at all four borders (stress set of SURVEY.md 8d: |flow| up to 3*md and
     beyond): border clamp identical to ATen clip_coordinates, zero flow-gradient where clipped."""
