@@ -165,6 +165,44 @@ def make_params(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor]
     return p
 
 
+_PARAM_CACHE: dict = {}
+
+
+def make_params_cached(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
+                       warp_mode, leaky_slope) -> CorrParams:
+    """`make_params` memoised on everything the block depends on (shapes, dtype, strides, configuration): building
+    the ctypes structure costs more host time than the launch itself.  The blocks are read-only after creation."""
+    key = (x1.shape, x1.dtype, x1.stride(), x2.stride(), None if flow is None else flow.stride(),
+           None if out is None else out.stride(), pad_size, kernel_size, max_displacement, stride1, stride2,
+           corr_multiply, warp_mode, leaky_slope)
+    p = _PARAM_CACHE.get(key)
+    if p is None:
+        if len(_PARAM_CACHE) > 4096:
+            _PARAM_CACHE.clear()
+        p = make_params(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
+                        warp_mode, leaky_slope)
+        _PARAM_CACHE[key] = p
+    return p
+
+
+class _NullGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def device_guard(device):
+    """Make `device` current for the call, without paying for a context switch when it already is."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NULL_GUARD
+    return torch.cuda.device(device)
+
+
 def output_dims(p: CorrParams):
     oc, oh, ow = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     check(lib().cerb_corr_output_dims(ctypes.byref(p), ctypes.byref(oc), ctypes.byref(oh), ctypes.byref(ow)),

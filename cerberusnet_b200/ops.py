@@ -6,13 +6,14 @@ Python and nothing here falls back to PyTorch ops.
 from __future__ import annotations
 
 import ctypes
+import functools
 from typing import Optional, Tuple
 
 import torch
 
 from . import _lib
-from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, check, current_stream_ptr, lib, make_params,
-                   output_dims, ptr, require_cuda)
+from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, check, current_stream_ptr,
+                   device_guard, lib, make_params_cached as make_params, output_dims, ptr, require_cuda)
 
 __all__ = ["warp_corr_forward", "warp_corr_forward_upflow", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
            "WARP_TORCH", "WARP_TRT", "WARP_TORCH_CPU"]
@@ -27,6 +28,12 @@ def _inner_contig(t: torch.Tensor) -> torch.Tensor:
 
 def corr_output_shape(x_shape, pad_size, kernel_size, max_displacement, stride1, stride2) -> Tuple[int, int, int, int]:
     """(B, D*D, outH, outW) by the reference rule (correlation_cuda.cpp:6-14)."""
+    return _corr_output_shape(tuple(x_shape), int(pad_size), int(kernel_size), int(max_displacement), int(stride1),
+                              int(stride2))
+
+
+@functools.lru_cache(maxsize=1024)
+def _corr_output_shape(x_shape, pad_size, kernel_size, max_displacement, stride1, stride2):
     B, C, H, W = x_shape
     p = _lib.CorrParams()
     p.batch, p.channels, p.height, p.width = B, C, H, W
@@ -63,7 +70,7 @@ def warp_corr_forward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.T
         raise CostVolumeError(f"out must be {shape} {x1.dtype} with unit W stride")
     p = make_params(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
                     warp_mode, leaky_slope)
-    with torch.cuda.device(x1.device):
+    with device_guard(x1.device):
         rc = lib().cerb_warp_corr_forward_variant(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow), ptr(out), int(variant),
                                                   ctypes.c_void_p(current_stream_ptr(x1.device)))
     check(rc, "cerb_warp_corr_forward")
@@ -102,7 +109,7 @@ def warp_corr_forward_upflow(x1: torch.Tensor, x2: torch.Tensor, flow_coarse: to
                     warp_mode, leaky_slope)
     cs = (ctypes.c_int64 * 4)(*flow_coarse.stride())
     us = (ctypes.c_int64 * 4)(*flow_up.stride())
-    with torch.cuda.device(x1.device):
+    with device_guard(x1.device):
         rc = lib().cerb_warp_corr_forward_upflow(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow_coarse), cs, ptr(flow_up), us,
                                                  ptr(out), ctypes.c_void_p(current_stream_ptr(x1.device)))
     check(rc, "cerb_warp_corr_forward_upflow")
@@ -130,7 +137,7 @@ def warp_corr_backward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.
     gflow = torch.empty(flow.shape, dtype=torch.float32, device=x1.device) if flow is not None else None
     need = lib().cerb_warp_corr_backward_workspace(ctypes.byref(p), 1 if flow is not None else 0)
     ws = torch.empty(need, dtype=torch.uint8, device=x1.device) if need else None
-    with torch.cuda.device(x1.device):
+    with device_guard(x1.device):
         rc = lib().cerb_warp_corr_backward(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow), ptr(out), ptr(grad_out),
                                            ptr(g1), ptr(g2), ptr(gflow), ptr(ws), need,
                                            ctypes.c_void_p(current_stream_ptr(x1.device)))
@@ -146,7 +153,7 @@ def flow_warp_forward(image: torch.Tensor, flow: torch.Tensor, warp_mode: int = 
     if flow.shape != (B, 2, H, W):
         raise CostVolumeError(f"flow must be (B,2,H,W), got {tuple(flow.shape)}")
     out = torch.empty_like(image)
-    with torch.cuda.device(image.device):
+    with device_guard(image.device):
         rc = lib().cerb_flow_warp_forward(ptr(image), ptr(flow), ptr(out), B, C, H, W, _lib.dtype_code(image),
                                           int(warp_mode), ctypes.c_void_p(current_stream_ptr(image.device)))
     check(rc, "cerb_flow_warp_forward")
@@ -161,7 +168,7 @@ def flow_warp_backward(image: torch.Tensor, flow: torch.Tensor, grad_out: torch.
     B, C, H, W = image.shape
     gimg = torch.empty_like(image)
     gflow = torch.empty_like(flow)
-    with torch.cuda.device(image.device):
+    with device_guard(image.device):
         rc = lib().cerb_flow_warp_backward(ptr(image), ptr(flow), ptr(grad_out), ptr(gimg), ptr(gflow), B, C, H, W,
                                            _lib.dtype_code(image), int(warp_mode),
                                            ctypes.c_void_p(current_stream_ptr(image.device)))
