@@ -257,6 +257,45 @@ def test_fused_flow_upsample_argument_checks():
         ops.warp_corr_forward_upflow(x, x, c[:, :, :4], 4, 1, 4, 1, 1)
 
 
+def _fuzz_cases(n, seed):
+    rs = np.random.RandomState(seed)
+    cases = []
+    for _ in range(n):
+        md = int(rs.choice([4, 4, 4, 5, 6, 8, 9]))
+        pad = int(rs.choice([md, md, md, max(0, md - 2), md + 1]))
+        B = int(rs.randint(1, 4)); C = int(rs.choice([1, 3, 8, 17, 32, 40, 64]))
+        H = int(rs.randint(2 * md + 2 - 2 * pad if pad < md else 2, 40)); W = int(rs.randint(2 * md + 2 - 2 * pad if pad < md else 2, 70))
+        H, W = max(H, 2 * (md - pad) + 2, 2), max(W, 2 * (md - pad) + 2, 2)
+        cases.append((B, C, H, W, pad, md, bool(rs.randint(0, 2)), float(rs.choice([0.5, 1.5, 4.0, 12.0])),
+                      int(rs.choice([0, 0, 1, 3])), None if rs.randint(0, 4) == 0 else 0.1))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(40, 2024), ids=lambda c: "B%dC%d_%dx%d_p%dmd%d_f%d_s%g_v%d_%s" % c)
+def test_fuzz_forward_backward_vs_oracle(case):
+    """Random shapes (odd sizes, single pixels rows, C not a multiple of anything), pads, displacements,
+    flow magnitudes (including ones that leave the raw box and the image), kernel variants."""
+    B, C, H, W, pad, md, with_flow, sigma, variant, slope = case
+    rs = np.random.RandomState(H * 1000 + W)
+    x1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    x2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+    flow = (rs.standard_normal((B, 2, H, W)) * sigma).astype(np.float32) if with_flow else None
+    ref = co.level_forward(x1, x2, flow, pad, 1, md, 1, 1, co.WARP_TORCH, slope)
+    t1, t2, tf = to_dev(x1, x2, flow)
+    out = ops.warp_corr_forward(t1, t2, tf, pad, 1, md, 1, 1, 1, cb.WARP_TORCH, slope, variant=variant)
+    assert out.shape == ref.shape
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    g = rs.standard_normal(ref.shape).astype(np.float32)
+    r1, r2, rf = co.level_backward(x1, x2, flow, g, pad, 1, md, 1, 1, co.WARP_TORCH, slope)
+    g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out if slope is not None else None, to_dev(g)[0], pad, 1, md, 1, 1, 1,
+                                        cb.WARP_TORCH, slope)
+    # LeakyReLU masks can differ where |out| is at rounding level: compare with the usual tolerance relative to max|ref|
+    assert rel_err(g1.cpu().numpy(), r1) < 2 * TOL
+    assert rel_err(g2.cpu().numpy(), r2) < 2 * TOL
+    if with_flow:
+        assert rel_err(gf.cpu().numpy(), rf) < 2 * TOL
+
+
 def test_flow_far_outside_every_border():
     """Samples clipped at all four borders (stress set of SURVEY.md 8d: |flow| up to 3*md and
     beyond): border clamp identical to ATen clip_coordinates, zero flow-gradient where clipped."""
