@@ -223,7 +223,9 @@ __device__ __forceinline__ Unit decode_unit(const FwdArgs& a, int tile) {
 }
 
 // ------------------------------------------------------------------ fast kernel ----------
-template <typename T, int TY, int TX, int KS, int CC, int RS>
+// UP: the flow is up-sampled on the fly from the next-coarser level (a separate instantiation, so the
+// plain path's prologue is not perturbed -- folding it in behind a runtime test cost 0.5 us per level)
+template <typename T, int TY, int TX, int KS, int CC, int RS, bool UP>
 __global__ void __launch_bounds__(FwdCfg<TY, TX, KS, CC, RS>::NTHREADS, 1)
 warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
                      const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_out,
@@ -290,7 +292,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const int pt = tid - Cfg::NCONS;
     const int pwarp = pt >> 5;
     const int lane = pt & 31;
-    const bool warped = a.flow != nullptr || a.cflow != nullptr;
+    const bool warped = UP || a.flow != nullptr;
     const bool raw16 = sizeof(T) == 2 && a.raw16;           // 16-bit inputs staged through the raw stage
     const bool reduce_bbox = (warped || raw16) && a.use_tma_raw;
     int red_par = 0;
@@ -430,7 +432,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         // unconditional loads from clamped (always valid) addresses -- loads left inside the
         // validity branches are issued one round trip at a time
         float fu[Cfg::POS_PER_THREAD], fv[Cfg::POS_PER_THREAD];
-        if (a.cflow != nullptr) {
+        if constexpr (UP) {
           // flow = interpolate(2 * coarse, scale_factor=2, bilinear, align_corners=True), evaluated per halo
           // position with ATen's arithmetic (upsample_bilinear2d: src = scale * dst, lambda = src - int(src));
           // doubling commutes exactly with the blend.  Tile-interior positions also write the result out.
@@ -479,7 +481,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
               up[a.fus[1]] = r[1];
             }
           }
-        } else if (warped) {
+        }
+        if (!UP && warped) {
           const float* fn = a.flow + (long long)n * g.fls[0];
 #pragma unroll
           for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
@@ -1070,7 +1073,7 @@ static int num_sms() {
   return n;
 }
 
-template <typename T, int TY, int TX, int KS, int CC, int RS>
+template <typename T, int TY, int TX, int KS, int CC, int RS, bool UP>
 static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
                                int force_no_tma, bool allow_csplit, cudaStream_t stream, const UpFlow* uf) {
   using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
@@ -1132,7 +1135,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   }
   if (sizeof(T) == 2)
     a.out_vec8 = (((uintptr_t)out & 15) == 0 && g.os[0] % 8 == 0 && g.os[1] % 8 == 0 && g.os[2] % 8 == 0) ? 1 : 0;
-  auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS>;
+  auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS, UP>;
   static bool attr_set = false;  // benign race: the attribute call is idempotent
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -1192,8 +1195,12 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
       const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8) * nwin * nwin;
       small = big_tiles < (long long)num_sms() * 3 / 4;
     }
-    if (small) return launch_fast<T, 4, 16, 4, 8, 2>(g, x1, x2, flow, out, no_tma, true, stream, uf);
-    return launch_fast<T, 8, 32, 1, 4, 3>(g, x1, x2, flow, out, no_tma, false, stream, uf);
+    if (uf != nullptr) {
+      if (small) return launch_fast<T, 4, 16, 4, 8, 2, true>(g, x1, x2, flow, out, no_tma, true, stream, uf);
+      return launch_fast<T, 8, 32, 1, 4, 3, true>(g, x1, x2, flow, out, no_tma, false, stream, uf);
+    }
+    if (small) return launch_fast<T, 4, 16, 4, 8, 2, false>(g, x1, x2, flow, out, no_tma, true, stream, uf);
+    return launch_fast<T, 8, 32, 1, 4, 3, false>(g, x1, x2, flow, out, no_tma, false, stream, uf);
   }
   if (uf != nullptr) return cudaErrorNotSupported;   // the generic kernel has no fused up-sampling
   const long long total = (long long)g.B * g.D2 * g.outH * g.outW;
