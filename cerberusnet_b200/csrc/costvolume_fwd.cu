@@ -308,6 +308,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         // halo tile of the second map: displacement window origin w covers displacements w-md .. w-md+8
         const int qy0 = iy0 + un.woy - g.md, qx0 = ix0 + un.wox - g.md;
         int path = (!warped && a.use_tma_x2) ? PATH_TMA_X2 : PATH_DIRECT, ox = 0, oy = 0;
+        // 16-bit inputs without a flow: the box is the halo tile itself, known without any bounding box
+        // (origin aligned down to 8 elements; coordinates outside the image are zero-filled by TMA)
+        const bool plain16 = raw16 && !warped && (qx0 & 3) == 0;
+        if (plain16) { path = PATH_RAW; ox = qx0 & ~7; oy = qy0; }
         // x1 does not depend on the flow: request the first stages' tiles while the gather warps
         // are still computing sample positions and the bounding box
         int x1_pre = 0;
@@ -319,7 +323,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             if (++xs == kStages) { xs = 0; xphase ^= 1; }
           }
         }
-        if (reduce_bbox) {
+        if (reduce_bbox && !plain16) {
           named_bar_sync(2, kProducerThreads);
           const int* rp = red + red_par * (kGatherWarps * 4);
           int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
@@ -421,6 +425,47 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           }
           ++titer;
           continue;
+        }
+
+        // ------------- 16-bit inputs, no flow: widen the TMA-loaded halo tile (and the x1 tile) -------------
+        if constexpr (sizeof(T) == 2) {
+          if (raw16 && !warped && (qx0 & 3) == 0) {
+            const int dxo = qx0 - (qx0 & ~7);   // 0 or 4: column of the halo origin inside the box
+            for (int ck = ck_begin; ck < ck_end; ++ck) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_wait(&raw_full[rc], rcphase);
+              const unsigned char* rs = (const unsigned char*)(raws + rc * Cfg::RAW_STAGE);
+              const uint4* x1r = reinterpret_cast<const uint4*>(rs + Cfg::RAW16_X1_OFF);
+              float* x1dst = x1s + stage * Cfg::X1_STAGE;
+              for (int e8 = gt; e8 < Cfg::X1_STAGE / 8; e8 += kGatherThreads) {
+                const uint4 pk = x1r[e8];
+                const T* hv = reinterpret_cast<const T*>(&pk);
+                const int e = e8 * 8, row = e / TX, x = e - row * TX;   // row = c * TY + y
+                *reinterpret_cast<float4*>(x1dst + row * TX + swz_chunk<TX>(row, x >> 2) * 4) =
+                    make_float4(to_f32<T>(hv[0]), to_f32<T>(hv[1]), to_f32<T>(hv[2]), to_f32<T>(hv[3]));
+                *reinterpret_cast<float4*>(x1dst + row * TX + swz_chunk<TX>(row, (x >> 2) + 1) * 4) =
+                    make_float4(to_f32<T>(hv[4]), to_f32<T>(hv[5]), to_f32<T>(hv[6]), to_f32<T>(hv[7]));
+              }
+              const T* __restrict__ src16 = reinterpret_cast<const T*>(rs);
+              float* __restrict__ x2dst = x2s + stage * Cfg::X2_STAGE;
+              constexpr int V_ROW = Cfg::HX / 4, U = Cfg::HY * V_ROW;
+              for (int u = gt; u < CC * U; u += kGatherThreads) {
+                const int c = u / U, r = u - c * U;
+                const int hy = r / V_ROW, v = r - hy * V_ROW;
+                const uint2 pk = *reinterpret_cast<const uint2*>(src16 + c * (Cfg::RAW_H * Cfg::RAW_W16) + hy * Cfg::RAW_W16 +
+                                                                 dxo + 4 * v);
+                const T* hv = reinterpret_cast<const T*>(&pk);
+                *reinterpret_cast<float4*>(x2dst + c * (Cfg::HY * Cfg::XS) + hy * Cfg::XS + 4 * v) =
+                    make_float4(to_f32<T>(hv[0]), to_f32<T>(hv[1]), to_f32<T>(hv[2]), to_f32<T>(hv[3]));
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&raw_empty[rc]);
+              if (++rc == RS) { rc = 0; rcphase ^= 1; }
+              publish_stage();
+            }
+            ++titer;
+            continue;
+          }
         }
 
         // ------------- per-position sampling data, fixed for the whole tile -------------
