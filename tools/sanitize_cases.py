@@ -30,6 +30,17 @@ for flow in (False, True):
         run(1, 24, 16, 32, flow, dtype=dt)                # 16-bit, 4x16 with cluster split
         run(2, 8, 19, 37, flow, dtype=dt)                 # 16-bit, no TMA (W % 8 != 0)
 run(1, 16, 32, 64, True, sigma=20.0, dtype=torch.bfloat16, variant=1)   # 16-bit raw box misfit
+# fused flow up-sampling (plain and cluster-split kernels, md 4 and 8), writing into a concat-buffer slice
+for (C, H, W, md) in ((16, 32, 64, 4), (48, 16, 32, 4), (8, 24, 40, 8)):
+    a = torch.randn(1, C, H, W, device=dev); coarse = torch.randn(1, 2, H // 2, W // 2, device=dev)
+    cat = torch.zeros(1, (2 * md + 1) ** 2 + 2, H, W, device=dev)
+    ops.warp_corr_forward_upflow(a, a, coarse, md, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1, out=cat[:, :-2], flow_up=cat[:, -2:])
+# more tiles than CTAs: persistent loop, per-column stores, 16-bit without a flow
+for dt in (torch.float32, torch.float16):
+    a = torch.randn(5, 4, 128, 256, device=dev).to(dt); fl = torch.randn(5, 2, 128, 256, device=dev)
+    ops.warp_corr_forward(a, a, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=1)
+    ops.warp_corr_forward(a, a, None, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=1)
+torch.cuda.synchronize()
 x = torch.randn(1, 6, 12, 20, device=dev); f = torch.randn(1, 2, 12, 20, device=dev) * 3
 o = ops.flow_warp_forward(x, f); ops.flow_warp_backward(x, f, torch.randn_like(o))
 ops.warp_corr_forward(x, x, f, 3, 3, 4, 2, 2); torch.cuda.synchronize()
