@@ -273,6 +273,10 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   // and stores its slice.
   const int S = a.csplit, Slog = a.csplit_log2;
   const int crank = S > 1 ? (int)cluster_ctarank() : 0;
+  // Distributed shared memory may only be touched once every CTA of the cluster is running: a split-phase
+  // cluster barrier -- arrive here (non-blocking), wait right before the first remote store in the epilogue,
+  // by which time it has long completed.
+  if (S > 1) cluster_arrive_release();
   const int tile0 = (int)blockIdx.x >> Slog, tile_step = (int)gridDim.x >> Slog;
   const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
   int titer = 0;
@@ -369,7 +373,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         ++titer;
       }
       pdl_launch_dependents();  // this role has issued its last copy: let the next kernel start launching
-      if (S > 1) { __syncwarp(); cluster_sync_all(); }  // pairs with the consumers' barrier (all threads of the cluster arrive)
+      if (S > 1) { __syncwarp(); cluster_wait_acquire(); cluster_sync_all(); }  // start-up phase, then the consumers' barrier (every thread of the cluster arrives)
     } else {
       // ---------------------------- gather warps ----------------------------
       const int gw = pwarp < kTmaWarp ? pwarp : pwarp - 1;  // 0 .. kGatherWarps-1
@@ -758,7 +762,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         ++titer;
       }
       pdl_launch_dependents();
-      if (S > 1) { __syncwarp(); cluster_sync_all(); }
+      if (S > 1) { __syncwarp(); cluster_wait_acquire(); cluster_sync_all(); }
     }
   } else {
     // =========================== CONSUMER WARPS ===========================
@@ -893,6 +897,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           float* recv = (float*)(smem + Cfg::SMEM_RECV);
           const int units = kUnits >> Slog;             // float4 units per slice (host guarantees divisibility)
           const uint32_t rbase = smem_u32(recv) + 16u * (uint32_t)(crank * units);
+          __syncwarp();
+          cluster_wait_acquire();                       // start-up phase: every CTA of the cluster is running
           for (int u = tid; u < kUnits; u += Cfg::NCONS) {
             float4 s4 = o4[u];
 #pragma unroll
