@@ -274,15 +274,18 @@ def main_gpu(args, rank, world, local_rank):
     reps = 20
     for li, (C, H, W, wp) in enumerate(PWC_LEVELS):
         g = capture(lambda: [launch_level(sets[s % N_SETS][li]) for s in range(N_SETS * 2)])
-        with torch.cuda.stream(stream):
-            g.replay()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(reps):
+        samples = []
+        for _ in range(5):   # median of 5 windows of 400 launches: one window is ~8 ms, short enough to catch a transient
+            with torch.cuda.stream(stream):
                 g.replay()
-            b.record(stream)
-        torch.cuda.synchronize()
-        us = a.elapsed_time(b) * 1e3 / (reps * N_SETS * 2)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    g.replay()
+                b.record(stream)
+            torch.cuda.synchronize()
+            samples.append(a.elapsed_time(b) * 1e3 / (reps * N_SETS * 2))
+        us = float(np.median(samples))
         byts, fl = level_bytes(C, H, W, wp), level_flops(C, H, W)
         level_stats.append({"level": li, "C": C, "H": H, "W": W, "warped": wp, "us_per_launch": round(us, 3),
                             "algorithmic_MB": round(byts / 1e6, 3), "GBps": round(byts / us / 1e3, 1),
@@ -297,7 +300,7 @@ def main_gpu(args, rank, world, local_rank):
         "traffic": NCU_TRAFFIC_BYTES_FINEST, "traffic_source": "profiles/r01_ncu_fwd_finest_level.txt", "peak_source": peak_src,
         "kernel": f"warp_corr_fwd_kernel<float,8,32,1,4,3> level {dom['level']} (C={dom['C']}, {dom['H']}x{dom['W']})",
         "algorithmic_bytes_per_launch": int(dom["algorithmic_MB"] * 1e6),
-        "avg_launch_us": dom["us_per_launch"],
+        "avg_launch_us": dom["us_per_launch"], "avg_launch_us_method": "median of 5 windows of 400 back-to-back launches (CUDA events on the launching stream)",
         "binding_roof_frac": round(max(t_hbm, t_fma) * 1e6 / dom["us_per_launch"], 4),
         "fma_peak_tflops": FMA_PEAK_TFLOPS, "fma_frac": dom["fma_frac"],
         "sum_level_us": round(sum(d["us_per_launch"] for d in level_stats), 3),
