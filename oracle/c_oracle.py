@@ -49,6 +49,7 @@ def lib() -> ctypes.CDLL:
         L.cvo_leaky_relu_backward.argtypes = [_f32p, _f32p, ctypes.c_size_t, ctypes.c_float]
         L.cvo_leaky_relu_backward.restype = None
         L.cvo_level_forward.argtypes = [_f32p] * 5 + [i] * 10 + [ctypes.c_float, i]
+        L.cvo_flow_upsample2x.argtypes = [_f32p, _f32p, i, i, i]
         _lib = L
     return _lib
 
@@ -117,6 +118,16 @@ def flow_warp_backward(img, flow, gout, mode=WARP_TORCH):
     _check(lib().cvo_flow_warp_backward(_p(img), _p(flow), _p(gout), _p(gimg), _p(gflow), B, C, H, W, mode),
            "flow_warp_backward")
     return gimg, gflow
+
+
+def flow_upsample2x(coarse) -> np.ndarray:
+    """F.interpolate(2 * coarse, scale_factor=2, mode='bilinear', align_corners=True) for a (B,2,Hc,Wc) flow."""
+    coarse = _c(coarse)
+    B, two, Hc, Wc = coarse.shape
+    assert two == 2
+    up = np.empty((B, 2, 2 * Hc, 2 * Wc), np.float32)
+    _check(lib().cvo_flow_upsample2x(_p(coarse), _p(up), B, Hc, Wc), "flow_upsample2x")
+    return up
 
 
 def leaky_relu(x, slope=0.1) -> np.ndarray:

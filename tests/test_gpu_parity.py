@@ -214,6 +214,21 @@ def test_fused_flow_upsample_matches_interpolate(shape, md, dtype):
     assert torch.equal(up2, ref_flow) and torch.equal(out2, ref_out)
 
 
+def test_fused_flow_upsample_vs_c_oracle():
+    """The fused entry against the CPU oracle chain (flow_upsample2x -> level_forward), independent of ATen's GPU kernels."""
+    rs = np.random.RandomState(17)
+    for (B, C, H, W) in ((1, 12, 16, 32), (2, 7, 24, 40)):
+        x1 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+        x2 = rs.standard_normal((B, C, H, W)).astype(np.float32)
+        coarse = (rs.standard_normal((B, 2, H // 2, W // 2)) * 1.5).astype(np.float32)
+        up_ref = co.flow_upsample2x(coarse)
+        ref = co.level_forward(x1, x2, up_ref, 4, 1, 4, 1, 1, co.WARP_TORCH, 0.1)
+        t1, t2, tc = to_dev(x1, x2, coarse)
+        out, up = ops.warp_corr_forward_upflow(t1, t2, tc, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
+        assert np.abs(up.cpu().numpy() - up_ref).max() <= 2e-6 * max(1.0, np.abs(up_ref).max())
+        assert rel_err(out.cpu().numpy(), ref) < TOL
+
+
 def test_fused_flow_upsample_autograd_and_decoder():
     """Gradients through the fused up-sampling equal those of the un-fused composition
     (interpolate -> fused warp+corr), and the decoder harness gives the same flows either way."""

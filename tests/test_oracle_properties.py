@@ -107,3 +107,32 @@ def test_leaky_relu():
     np.testing.assert_allclose(co.leaky_relu(x, 0.1), [-0.2, 0.0, 0.0, 3.0], rtol=1e-7)
     y = co.leaky_relu(x, 0.1)
     np.testing.assert_allclose(co.leaky_relu_backward(y, np.ones(4, np.float32), 0.1), [0.1, 0.1, 0.1, 1.0], rtol=1e-7)
+
+
+def test_flow_upsample_restatement_matches_aten():
+    """the C restatement of `F.interpolate(2*flow, scale_factor=2, 'bilinear', align_corners=True)`
+    (pwcnet_sfd.py:176) against ATen's CPU kernel, and its composition with the level oracle against the
+    un-fused composition -- the oracle the GPU test of cerb_warp_corr_forward_upflow leans on."""
+    rs = np.random.RandomState(3)
+    for (B, Hc, Wc) in ((1, 2, 2), (2, 5, 9), (1, 8, 16), (3, 16, 12)):
+        coarse = rs.standard_normal((B, 2, Hc, Wc)).astype(np.float32) * 2.0
+        want = torch.nn.functional.interpolate(torch.from_numpy(coarse) * 2, scale_factor=2, mode="bilinear",
+                                               align_corners=True).numpy()
+        got = co.flow_upsample2x(coarse)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 2e-6 * max(1.0, np.abs(want).max())
+    # exactness where it must be exact: a constant field stays constant (x2), corners are the coarse corners (x2)
+    const = np.full((1, 2, 4, 6), 0.75, np.float32)
+    assert np.all(co.flow_upsample2x(const) == 1.5)
+    up = co.flow_upsample2x(coarse)
+    assert np.array_equal(up[:, :, 0, 0], 2 * coarse[:, :, 0, 0]) and np.array_equal(up[:, :, -1, -1], 2 * coarse[:, :, -1, -1])
+    # composed level: warp by the up-sampled flow
+    x1 = rs.standard_normal((1, 6, 16, 24)).astype(np.float32)
+    x2 = rs.standard_normal((1, 6, 16, 24)).astype(np.float32)
+    cf = rs.standard_normal((1, 2, 8, 12)).astype(np.float32)
+    a = co.level_forward(x1, x2, co.flow_upsample2x(cf))
+    b = to.level_forward(torch.from_numpy(x1), torch.from_numpy(x2),
+                         torch.nn.functional.interpolate(torch.from_numpy(cf) * 2, scale_factor=2, mode="bilinear",
+                                                         align_corners=True), warp_mode=to.WARP_TORCH_CPU).numpy()
+    a_cpu = co.level_forward(x1, x2, co.flow_upsample2x(cf), warp_mode=co.WARP_TORCH_CPU)
+    assert rel_err(a_cpu, b) < 1e-5 and a.shape == b.shape
