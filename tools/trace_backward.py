@@ -1,3 +1,4 @@
+"""clock64 trace of one CTA of each correlation-backward kernel: python tools/trace_backward.py B none|leaky flow|noflow"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch, torch.nn.functional as F
@@ -17,8 +18,9 @@ lib.cerb_debug_set_trace_buffer(ctypes.c_void_p(tr.data_ptr()))
 ops.warp_corr_backward(x1, x2, fl, out, g, 4, 1, 4, 1, 1, 1, 0, SLOPE); torch.cuda.synchronize()
 lib.cerb_debug_set_trace_buffer(None)
 t = tr.cpu().numpy()
-names = ["start", "G tile built", "S chunk0 staged", "chunk0 contraction done", "chunk0 out staged", "all chunks written", "G batch0", "G batch1", "G batch2"]
+names = {0: "start (window 0)", 6: "G tile fetched + masked", 1: "chunk 0: barrier passed", 2: "chunk 0: S halo staged",
+         3: "chunk 0: contraction done", 4: "chunk 0: output staged", 5: "all windows / chunks written"}
 for w in (0, 1):
-    print("kernel WHICH =", w)
-    for i, nm in enumerate(names):
-        print(f"   {nm:26s} +{int(t[w*32+i]-t[w*32]):8d} cyc")
+    print("kernel WHICH =", w, "(grad wrt x1)" if w == 0 else "(grad wrt the second correlation input)")
+    for i, nm in sorted(names.items(), key=lambda kv: t[w * 32 + kv[0]]):
+        print(f"   {nm:30s} +{int(t[w*32+i]-t[w*32]):8d} cyc")
