@@ -28,7 +28,7 @@ class CorrParams(ctypes.Structure):
         ("pad_size", ctypes.c_int32), ("kernel_size", ctypes.c_int32), ("max_displacement", ctypes.c_int32),
         ("stride1", ctypes.c_int32), ("stride2", ctypes.c_int32), ("corr_multiply", ctypes.c_int32),
         ("dtype", ctypes.c_int32), ("warp_mode", ctypes.c_int32), ("leaky_slope", ctypes.c_float),
-        ("reserved", ctypes.c_int32),
+        ("x2_batch_roll", ctypes.c_int32),
         ("x1_stride", ctypes.c_int64 * 4), ("x2_stride", ctypes.c_int64 * 4),
         ("flow_stride", ctypes.c_int64 * 4), ("out_stride", ctypes.c_int64 * 4),
     ]
@@ -148,7 +148,7 @@ def _strides(t: Optional[torch.Tensor]):
 
 def make_params(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor],
                 pad_size: int, kernel_size: int, max_displacement: int, stride1: int, stride2: int,
-                corr_multiply: int, warp_mode: int, leaky_slope: Optional[float]) -> CorrParams:
+                corr_multiply: int, warp_mode: int, leaky_slope: Optional[float], x2_roll: int = 0) -> CorrParams:
     B, C, H, W = x1.shape
     p = CorrParams()
     p.batch, p.channels, p.height, p.width = B, C, H, W
@@ -157,7 +157,7 @@ def make_params(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor]
     p.dtype = dtype_code(x1)
     p.warp_mode = int(warp_mode)
     p.leaky_slope = math.nan if leaky_slope is None else float(leaky_slope)
-    p.reserved = 0
+    p.x2_batch_roll = int(x2_roll)
     p.x1_stride = _strides(x1)
     p.x2_stride = _strides(x2)
     p.flow_stride = _strides(flow)
@@ -169,18 +169,18 @@ _PARAM_CACHE: dict = {}
 
 
 def make_params_cached(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
-                       warp_mode, leaky_slope) -> CorrParams:
+                       warp_mode, leaky_slope, x2_roll=0) -> CorrParams:
     """`make_params` memoised on everything the block depends on (shapes, dtype, strides, configuration): building
     the ctypes structure costs more host time than the launch itself.  The blocks are read-only after creation."""
     key = (x1.shape, x1.dtype, x1.stride(), x2.stride(), None if flow is None else flow.stride(),
            None if out is None else out.stride(), pad_size, kernel_size, max_displacement, stride1, stride2,
-           corr_multiply, warp_mode, leaky_slope)
+           corr_multiply, warp_mode, leaky_slope, x2_roll)
     p = _PARAM_CACHE.get(key)
     if p is None:
         if len(_PARAM_CACHE) > 4096:
             _PARAM_CACHE.clear()
         p = make_params(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
-                        warp_mode, leaky_slope)
+                        warp_mode, leaky_slope, x2_roll)
         _PARAM_CACHE[key] = p
     return p
 

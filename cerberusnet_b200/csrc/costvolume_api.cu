@@ -31,7 +31,7 @@ static int build_geom(const cerb_corr_params* p, bool has_flow, Geom& g) {
   if (p->pad_size < 0 || p->kernel_size < 1 || p->max_displacement < 0 || p->stride1 < 1 || p->stride2 < 1)
     return CERB_EINVAL;
   if (p->dtype != CERB_F32 && p->dtype != CERB_F16 && p->dtype != CERB_BF16) return CERB_EINVAL;
-  if (p->reserved != 0) return CERB_EINVAL;
+  if (p->x2_batch_roll < 0 || p->x2_batch_roll >= p->batch) return CERB_EINVAL;
   if (has_flow) {
     if (p->warp_mode < CERB_WARP_TORCH || p->warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
     if (p->height < 2 || p->width < 2) return CERB_EINVAL;  // grid normalisation divides by size-1
@@ -50,6 +50,7 @@ static int build_geom(const cerb_corr_params* p, bool has_flow, Geom& g) {
   g.has_act = (p->leaky_slope == p->leaky_slope) && p->leaky_slope >= 0.f;  // NaN / negative = off
   g.slope = g.has_act ? p->leaky_slope : 1.f;
   g.unnorm_fma = 1;
+  g.x2roll = p->x2_batch_roll;
   bool ok1, ok2, ok3, ok4;
   fill_strides(p->x1_stride, g.x1s, g.C, g.H, g.W, ok1);
   fill_strides(p->x2_stride, g.x2s, g.C, g.H, g.W, ok2);

@@ -40,7 +40,16 @@ struct Geom {
   float slope;
   int unnorm_fma;            // ATen un-normalise ((g+1)*size-1)/2 contracted to one FMA (nvcc -fmad) or not
   long long x1s[3], x2s[3], fls[3], os[3];  // N, C, H strides in elements (W stride == 1)
+  int x2roll;                // batch item n of x1 / flow / out is paired with item (n + x2roll) mod B of x2
 };
+
+// Batch item of the second map paired with item n (cerb_corr_params.x2_batch_roll): with x1 = x2 = the features of
+// [image 1; image 2] and a roll of B/2, one launch computes both flow directions of the reference's
+// `consistency=True` forward (nnet_models/pwcnet.py:108-113, cerberus.py:131-135) without copying a feature map.
+__host__ __device__ __forceinline__ int x2_item(const Geom& g, int n) {
+  const int m = n + g.x2roll;
+  return m >= g.B ? m - g.B : m;
+}
 
 // ---------------------------------------------------------------- flow warp ---------------
 // a / c correctly rounded (Markstein: q = a*rc, r = a - q*c exact by FMA, q' = q + r*rc) for a
@@ -166,6 +175,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Wait with a suspend-time hint (ns): a waiting warp may sleep in hardware up to that long per attempt instead of
+// re-polling; used by roles that typically wait long (consumers on `full`) so their polling does not compete with
+// the staging warps' shared-memory traffic.
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "HWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra.uni HWAIT_DONE;\n\t"
+      "bra.uni HWAIT_LOOP;\n\t"
+      "HWAIT_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(hint_ns)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(sleep_ns);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -273,6 +310,16 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
+}
+// scalar shared-memory access by 32-bit shared address: a constant added to `addr` folds into the instruction's
+// immediate offset (LDS R, [R + imm])
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");

@@ -47,7 +47,8 @@ long long* get_trace_buffer() { return g_trace_buffer; }
 static int g_trace_iter = 0;
 void set_trace_iter(int it) { g_trace_iter = it; }
 // records only the `dbg_iter`-th tile processed by each CTA (every role keeps its own `titer`)
-#define CERB_TRACE(slot) do { if (a.dbg && titer == a.dbg_iter) a.dbg[(long long)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+constexpr int kTraceSlots = 192;  // clock64 slots per CTA in the debugging trace
+#define CERB_TRACE(slot) do { if (a.dbg && titer == a.dbg_iter) a.dbg[(long long)blockIdx.x * kTraceSlots + (slot)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------ configuration --------
 constexpr int kMD = 4;
@@ -55,21 +56,38 @@ constexpr int kD = 2 * kMD + 1;  // 9
 constexpr int kD2 = kD * kD;     // 81
 constexpr int kProducerThreads = 224;  // 7 staging warps (16 warps total = 4 per SMSP -> 128 regs)
 constexpr int kProducerWarps = kProducerThreads / 32;
-constexpr int kGatherWarps = kProducerWarps - 1;    // one staging warp only issues TMA
-// Which staging warp issues the TMA copies.  It heads the pipeline, so its issue latency matters:
-// measured on the finest PWC level, staging warp 0 (CTA warp 9, on a sub-partition with two
-// consumer warps) 19.0 us vs staging warp 3 (CTA warp 12, sharing a sub-partition with three
-// consumer warps) 22.8 us.
-#ifndef CERB_AB_TMAWARP
-#define CERB_AB_TMAWARP 0
+// Two staging warps only issue TMA copies (one elected lane each): a cp.async.bulk.tensor issue occupies its
+// thread for 350-700 cycles whatever the box size (tools/microbench/tma.cu: ~566 cycles per box from one
+// thread, aggregate rate scales with the number of issuing warps), so the raw x2 boxes and the x1 / plain x2
+// tiles go out from different warps.  Staging warp w is CTA warp 9 + w: warp 9 heads the pipeline (raw boxes)
+// and sits on a sub-partition with two consumer warps; the x1 issuer runs ahead of everyone and is parked on
+// the sub-partition that hosts three consumer warps.
+#ifndef CERB_AB_T0
+#define CERB_AB_T0 0
+#endif
+#ifndef CERB_AB_T1
+#define CERB_AB_T1 3
 #endif
 #ifndef CERB_AB_PIPE
 #define CERB_AB_PIPE 1
 #endif
-constexpr int kTmaWarp = CERB_AB_TMAWARP;
+constexpr int kTmaWarp = CERB_AB_T0;    // raw x2 source boxes (and, for 16-bit inputs, the x1 tile that rides with them)
+constexpr int kTmaWarp2 = CERB_AB_T1;   // x1 tiles, un-warped x2 halo tiles
+constexpr int kGatherWarps = kProducerWarps - 2;
+constexpr int kBboxThreads = (kGatherWarps + 1) * 32;   // gather warps + the raw-box issuer meet on named barrier 2
 
 constexpr int kGatherThreads = kGatherWarps * 32;
-constexpr int kStages = 3;     // x1 / warped-x2 stages
+// x1 / warped-x2 pipeline stages: 3 for the split-channel 4x16 configuration; the 8x32 configuration stores its
+// accumulators straight to global memory (no staged output tile), which leaves room for a deeper pipeline
+#ifndef CERB_AB_ST1
+#define CERB_AB_ST1 4
+#endif
+#ifndef CERB_AB_RS1
+#define CERB_AB_RS1 3
+#endif
+#ifndef CERB_AB_CC1
+#define CERB_AB_CC1 4
+#endif
 constexpr int kRawMargin = 6;  // flow variation (px) inside one halo tile the raw box absorbs
 constexpr int kCBatch = 1;     // direct-gather fallback: channels per software-pipelined batch
 
@@ -79,6 +97,8 @@ enum { PATH_TMA_X2 = 0, PATH_RAW = 1, PATH_DIRECT = 2 };
 template <int TY, int TX, int KS, int CC_, int RS_>
 struct FwdCfg {
   static constexpr int CC = CC_;   // channels per pipeline stage
+  static constexpr int ST = (KS == 1) ? CERB_AB_ST1 : 3;   // x1 / warped-x2 stages
+  static constexpr bool DIRECT_OUT = (KS == 1);   // accumulators -> global memory without a staged tile
   static constexpr int RS = RS_;   // raw x2 source boxes (TMA) in flight
   static constexpr int NSTRIP = TX / 8;
   static constexpr int COMBOS = TY * kD;
@@ -104,14 +124,14 @@ struct FwdCfg {
   static constexpr int RAW_STAGE = CC * RAW_H * RAW_W;  // floats
   static constexpr int OUT_TILE = kD2 * TY * TX;       // floats, one partial buffer
   static constexpr size_t SMEM_X1 = 0;
-  static constexpr size_t SMEM_X2 = SMEM_X1 + sizeof(float) * kStages * X1_STAGE;
-  static constexpr size_t SMEM_RAW = (SMEM_X2 + sizeof(float) * kStages * X2_STAGE + 127) / 128 * 128;
+  static constexpr size_t SMEM_X2 = SMEM_X1 + sizeof(float) * ST * X1_STAGE;
+  static constexpr size_t SMEM_RAW = (SMEM_X2 + sizeof(float) * ST * X2_STAGE + 127) / 128 * 128;
   static constexpr size_t SMEM_OUT = (SMEM_RAW + sizeof(float) * RS * RAW_STAGE + 1023) / 1024 * 1024;
   // cluster channel split: slices of the other CTAs' partial tiles are pushed here (KS > 1 only)
-  static constexpr size_t SMEM_RECV = SMEM_OUT + sizeof(float) * KS * OUT_TILE;
+  static constexpr size_t SMEM_RECV = SMEM_OUT + (DIRECT_OUT ? 0 : sizeof(float) * KS * OUT_TILE);
   static constexpr size_t SMEM_RED = SMEM_RECV + (KS > 1 ? sizeof(float) * OUT_TILE : 0);
   static constexpr size_t SMEM_BAR = SMEM_RED + sizeof(int) * 2 * kProducerWarps * 4;  // (kGatherWarps rows used)
-  static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * kStages + 2 * RS + 2) * sizeof(uint64_t) + 1024;
+  static constexpr size_t SMEM_BYTES = SMEM_BAR + (2 * ST + 2 * RS + 2) * sizeof(uint64_t) + 1024;
   static_assert(NCONS % 32 == 0, "consumer threads must be whole warps");
   static_assert((sizeof(float) * X1_STAGE) % 1024 == 0, "x1 stage must keep 1024-byte alignment");
   static_assert((sizeof(float) * X2_STAGE) % 128 == 0 && (sizeof(float) * RAW_STAGE) % 128 == 0, "TMA dst alignment");
@@ -152,6 +172,26 @@ template <int TY> __device__ __forceinline__ void combo_of(int idx, int& y, int&
 template <> __device__ __forceinline__ void combo_of<8>(int idx, int& y, int& d) { y = c_lut8.y[idx]; d = c_lut8.d[idx]; }
 template <> __device__ __forceinline__ void combo_of<4>(int idx, int& y, int& d) { y = c_lut4.y[idx]; d = c_lut4.d[idx]; }
 
+// 8 consecutive output pixels of one row: two 16-byte stores (fp32) or one (16-bit)
+template <typename T>
+__device__ __forceinline__ void store_row8(T* p, const float (&v)[8], bool wide) {
+  if constexpr (sizeof(T) == 4) {
+    if (wide) {   // one 256-bit store (STG.256, sm_100): a full 32-byte sector per thread, a full 128-byte line per 4 strips
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                   "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    } else {
+      asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+      asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    }
+  } else {
+    uint4 pk;
+    T* hv = reinterpret_cast<T*>(&pk);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hv[k] = from_f32<T>(v[k]);
+    *reinterpret_cast<uint4*>(p) = pk;
+  }
+}
+
 struct FwdArgs {
   Geom g;
   const void* x1;
@@ -167,7 +207,7 @@ struct FwdArgs {
   int use_tma_raw;  // raw x2 source boxes by TMA, warp gathered from shared memory
   int use_tma_out;  // output tile by TMA store
   int raw16;        // 16-bit inputs: raw x2 box and x1 tile by TMA as 16-bit data, converted by the gather warps
-  int out_vec8;     // 16-bit output: 16-byte stores straight from the staged tile
+  int out_vec8;     // output rows may be written with 16-byte stores (base and N/C/H strides 16-byte aligned)
   // fused flow up-sampling: coarse flow in, up-sampled flow out (cflow == nullptr: off)
   const float* cflow;
   long long cfs[3];
@@ -241,8 +281,8 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   float* outs = (float*)(smem + Cfg::SMEM_OUT);
   int* red = (int*)(smem + Cfg::SMEM_RED);
   uint64_t* full_bar = (uint64_t*)(smem + Cfg::SMEM_BAR);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* raw_full = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + Cfg::ST;
+  uint64_t* raw_full = empty_bar + Cfg::ST;
   uint64_t* raw_empty = raw_full + RS;
 
   const Geom& g = a.g;
@@ -251,7 +291,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   const T* __restrict__ x2 = (const T*)a.x2;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < Cfg::ST; ++s) {
       mbar_init(&full_bar[s], 1 + kGatherWarps);  // TMA thread (+tx bytes) and one arrival per gather warp
       mbar_init(&empty_bar[s], Cfg::NCONS / 32);
     }
@@ -280,7 +320,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
   const int tile0 = (int)blockIdx.x >> Slog, tile_step = (int)gridDim.x >> Slog;
   const int ck_begin = (crank * a.nchunks) >> Slog, ck_end = ((crank + 1) * a.nchunks) >> Slog;
   int titer = 0;
-  if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 0] = clock64();
+  if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * kTraceSlots + 0] = clock64();
   // PDL: everything above (barrier init, descriptor prefetch, cluster sync) overlapped the tail of
   // the previous kernel in the stream; inputs may be its outputs, so wait before the first read.
   pdl_wait();
@@ -301,34 +341,54 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     const bool reduce_bbox = (warped || raw16) && a.use_tma_raw;
     int red_par = 0;
 
-    if (pwarp == kTmaWarp) {
-      // ---------------------------- TMA warp ----------------------------
-      int ri = 0, xs = 0;
-      uint32_t riphase = 0, xphase = 0;
+    if (pwarp == kTmaWarp2) {
+      // ---------------------------- TMA warp: x1 tiles, un-warped x2 halo tiles ----------------------------
+      // Depends on nothing but free stages, so it runs ahead of the flow / bounding-box work of the tile.
+      int xs = 0;
+      uint32_t xphase = 0;
+      const bool plain_x2 = !warped && a.use_tma_x2;
+      for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
+        const Unit un = decode_unit<TY, TX>(a, tile);
+        const int n = un.n;
+        const int iy0 = un.by0 + a.off, ix0 = un.bx0 + a.off;
+        const int qy0 = iy0 + un.woy - g.md, qx0 = ix0 + un.wox - g.md;
+        if (lane == 0) {
+          for (int ck = ck_begin; ck < ck_end; ++ck) {
+            mbar_wait(&empty_bar[xs], xphase ^ 1);
+            if (ck < 6) CERB_TRACE(64 + 8 * ck + 3);
+            const uint32_t tx = (a.use_tma_in ? (uint32_t)(sizeof(float) * Cfg::X1_STAGE) : 0u) +
+                                (plain_x2 ? (uint32_t)(sizeof(float) * Cfg::X2_STAGE) : 0u);
+            if (tx) mbar_arrive_expect_tx(&full_bar[xs], tx);
+            else mbar_arrive(&full_bar[xs]);
+            if (a.use_tma_in) tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, ck * CC, n);
+            if (plain_x2) tma_load_4d(x2s + xs * Cfg::X2_STAGE, &tm_x2, &full_bar[xs], qx0, qy0, ck * CC, x2_item(g, n));
+            if (++xs == Cfg::ST) { xs = 0; xphase ^= 1; }
+            if (ck < 6) CERB_TRACE(64 + 8 * ck + 4);
+            if (ck < 8) CERB_TRACE(2 + ck);
+          }
+        }
+        __syncwarp();
+        ++titer;
+      }
+      pdl_launch_dependents();  // this role has issued its last copy: let the next kernel start launching
+      if (S > 1) { __syncwarp(); cluster_wait_acquire(); cluster_sync_all(); }  // start-up phase, then the consumers' barrier (every thread of the cluster arrives)
+    } else if (pwarp == kTmaWarp) {
+      // ---------------------------- TMA warp: raw x2 source boxes ----------------------------
+      int ri = 0;
+      uint32_t riphase = 0;
       for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
         const Unit un = decode_unit<TY, TX>(a, tile);
         const int n = un.n;
         const int iy0 = un.by0 + a.off, ix0 = un.bx0 + a.off;
         // halo tile of the second map: displacement window origin w covers displacements w-md .. w-md+8
         const int qy0 = iy0 + un.woy - g.md, qx0 = ix0 + un.wox - g.md;
-        int path = (!warped && a.use_tma_x2) ? PATH_TMA_X2 : PATH_DIRECT, ox = 0, oy = 0;
+        int path = PATH_DIRECT, ox = 0, oy = 0;
         // 16-bit inputs without a flow: the box is the halo tile itself, known without any bounding box
         // (origin aligned down to 8 elements; coordinates outside the image are zero-filled by TMA)
         const bool plain16 = raw16 && !warped && (qx0 & 3) == 0;
         if (plain16) { path = PATH_RAW; ox = qx0 & ~7; oy = qy0; }
-        // x1 does not depend on the flow: request the first stages' tiles while the gather warps
-        // are still computing sample positions and the bounding box
-        int x1_pre = 0;
-        if (reduce_bbox && a.use_tma_in && lane == 0) {
-          for (; x1_pre < kStages && ck_begin + x1_pre < ck_end; ++x1_pre) {
-            mbar_wait(&empty_bar[xs], xphase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[xs], (uint32_t)(sizeof(float) * Cfg::X1_STAGE));
-            tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, (ck_begin + x1_pre) * CC, n);
-            if (++xs == kStages) { xs = 0; xphase ^= 1; }
-          }
-        }
         if (reduce_bbox && !plain16) {
-          named_bar_sync(2, kProducerThreads);
+          named_bar_sync(2, kBboxThreads);
           const int* rp = red + red_par * (kGatherWarps * 4);
           int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
 #pragma unroll
@@ -342,41 +402,32 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           if (raw16) ox = xmin & ~7;
           if (xmin <= xmax && xmax - ox < (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W) && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
         }
-        if (lane == 0) {
+        if (lane == 0 && path == PATH_RAW) {
           for (int ck = ck_begin; ck < ck_end; ++ck) {
-            if (path == PATH_RAW) {
-              mbar_wait(&raw_empty[ri], riphase ^ 1);
-              if (raw16) {
-                unsigned char* rs = (unsigned char*)(raws + ri * Cfg::RAW_STAGE);
-                mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(Cfg::RAW16_BOX_BYTES + Cfg::RAW16_X1_BYTES));
-                tma_load_4d(rs, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
-                tma_load_4d(rs + Cfg::RAW16_X1_OFF, &tm_x1, &raw_full[ri], ix0, iy0, ck * CC, n);
-              } else {
-                mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
-                tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, n);
-              }
-              if (++ri == RS) { ri = 0; riphase ^= 1; }
+            if (ck < 6) CERB_TRACE(64 + 8 * ck + 0);
+            mbar_wait(&raw_empty[ri], riphase ^ 1);
+            if (ck < 6) CERB_TRACE(64 + 8 * ck + 1);
+            if (raw16) {
+              unsigned char* rs = (unsigned char*)(raws + ri * Cfg::RAW_STAGE);
+              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(Cfg::RAW16_BOX_BYTES + Cfg::RAW16_X1_BYTES));
+              tma_load_4d(rs, &tm_raw, &raw_full[ri], ox, oy, ck * CC, x2_item(g, n));
+              tma_load_4d(rs + Cfg::RAW16_X1_OFF, &tm_x1, &raw_full[ri], ix0, iy0, ck * CC, n);
+            } else {
+              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
+              tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, x2_item(g, n));
             }
-            if (ck - ck_begin < x1_pre) continue;  // x1 tile already requested above
-            mbar_wait(&empty_bar[xs], xphase ^ 1);
-            const uint32_t tx = (a.use_tma_in ? (uint32_t)(sizeof(float) * Cfg::X1_STAGE) : 0u) +
-                                (path == PATH_TMA_X2 ? (uint32_t)(sizeof(float) * Cfg::X2_STAGE) : 0u);
-            if (tx) mbar_arrive_expect_tx(&full_bar[xs], tx);
-            else mbar_arrive(&full_bar[xs]);
-            if (a.use_tma_in) tma_load_4d(x1s + xs * Cfg::X1_STAGE, &tm_x1, &full_bar[xs], ix0, iy0, ck * CC, n);
-            if (path == PATH_TMA_X2) tma_load_4d(x2s + xs * Cfg::X2_STAGE, &tm_x2, &full_bar[xs], qx0, qy0, ck * CC, n);
-            if (++xs == kStages) { xs = 0; xphase ^= 1; }
-            if (ck < 8) CERB_TRACE(2 + ck);
+            if (++ri == RS) { ri = 0; riphase ^= 1; }
+            if (ck < 6) CERB_TRACE(64 + 8 * ck + 2);
           }
         }
         __syncwarp();
         ++titer;
       }
-      pdl_launch_dependents();  // this role has issued its last copy: let the next kernel start launching
-      if (S > 1) { __syncwarp(); cluster_wait_acquire(); cluster_sync_all(); }  // start-up phase, then the consumers' barrier (every thread of the cluster arrives)
+      pdl_launch_dependents();
+      if (S > 1) { __syncwarp(); cluster_wait_acquire(); cluster_sync_all(); }
     } else {
       // ---------------------------- gather warps ----------------------------
-      const int gw = pwarp < kTmaWarp ? pwarp : pwarp - 1;  // 0 .. kGatherWarps-1
+      const int gw = pwarp - (pwarp > kTmaWarp ? 1 : 0) - (pwarp > kTmaWarp2 ? 1 : 0);  // 0 .. kGatherWarps-1
       const int gt = gw * 32 + lane;                        // 0 .. kGatherThreads-1
       int rc = 0;
       uint32_t rcphase = 0;
@@ -410,7 +461,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       auto publish_stage = [&]() {
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg::ST) { stage = 0; phase ^= 1; }
       };
 
       for (int tile = tile0; tile < a.total_tiles; tile += tile_step) {
@@ -474,7 +525,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
         // ------------- per-position sampling data, fixed for the whole tile -------------
         Taps taps[Cfg::POS_PER_THREAD];   // off[] first holds {x0, x1c, y0, y1c}, then offsets
-        int sdst[Cfg::POS_PER_THREAD];    // smem float offset inside a channel plane, -1 = no position
+        int sdst[Cfg::POS_PER_THREAD];    // smem float offset inside a channel plane (surplus slots: a padding column)
         unsigned valid_mask = 0;
         int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
         // every flow vector this thread needs is requested before the first one is used:
@@ -552,7 +603,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           const bool in_tile = i < Cfg::NPOS;
           const bool valid = in_tile && qy >= 0 && qy < g.H && qx >= 0 && qx < g.W;
           const int cy = min(max(qy, 0), g.H - 1), cx = min(max(qx, 0), g.W - 1);
-          sdst[j] = in_tile ? hy * Cfg::XS + hx : -1;
+          sdst[j] = in_tile ? hy * Cfg::XS + hx : Cfg::HX;   // surplus slots write a padding column nobody reads
           float sx = (float)cx, sy = (float)cy;   // un-warped: the pixel itself (weights 1,0,0,0)
           if (warped) {
             bool in_x, in_y;
@@ -584,7 +635,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             rp[gw * 4 + 0] = xmin; rp[gw * 4 + 1] = xmax;
             rp[gw * 4 + 2] = ymin; rp[gw * 4 + 3] = ymax;
           }
-          named_bar_sync(2, kProducerThreads);
+          named_bar_sync(2, kBboxThreads);
 #pragma unroll
           for (int w = 0; w < kGatherWarps; ++w) {
             xmin = min(xmin, rp[w * 4 + 0]); xmax = max(xmax, rp[w * 4 + 1]);
@@ -610,11 +661,99 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 
         if (path == PATH_RAW) {
           // ------------- warp gathered from the raw source box in shared memory -------------
+          if constexpr (sizeof(T) == 4) {
+            // Lean, software-pipelined gather.  Everything that does not change with the channel sits in registers
+            // as a shared-memory byte address (tap sources, destination): per channel a tap is one LDS with an
+            // immediate offset, a sample 1 FMUL + 3 FFMA + 1 select + 1 STS.  (The plain indexed form cost ~40
+            // instructions per sample, mostly address arithmetic and convergence barriers around predicated stores.)
+            // Channel batches are double-buffered ACROSS chunks: the taps of the next batch -- the first batch of the
+            // next chunk included, behind its raw_full wait -- are requested before the current batch is blended
+            // and stored, so neither an LDS round trip nor the barrier hand-over sits between two batches.
+#ifdef CERB_AB_CB
+            constexpr int CB = CERB_AB_CB;
+#else
+            constexpr int CB = 1;   // one channel per batch: 16 taps in flight per thread; two channels per batch spilled (128-register cap) and measured 12 % slower
+#endif
+            constexpr int NBAT = CC / CB;
+            static_assert(CC % CB == 0 && NBAT % 2 == 0, "an even number of channel batches per stage");
+            constexpr uint32_t kRawPlane = sizeof(float) * Cfg::RAW_H * Cfg::RAW_W;
+            constexpr uint32_t kDstPlane = sizeof(float) * Cfg::HY * Cfg::XS;
+            const uint32_t raw0 = smem_u32(raws), dst0 = smem_u32(x2s);
+            uint32_t ta[Cfg::POS_PER_THREAD][4], da[Cfg::POS_PER_THREAD];
+            float tv[2][CB][Cfg::POS_PER_THREAD][4];
+            auto set_sources = [&](int rstage) {
+              const uint32_t rbase = raw0 + (uint32_t)rstage * (uint32_t)(sizeof(float) * Cfg::RAW_STAGE);
+#pragma unroll
+              for (int j = 0; j < Cfg::POS_PER_THREAD; ++j)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ta[j][k] = rbase + ((uint32_t)taps[j].off[k] << 2);  // off = 0 for invalid positions
+            };
+            auto load_batch = [&](int b, float (&dst)[CB][Cfg::POS_PER_THREAD][4]) {
+#pragma unroll
+              for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                for (int j = 0; j < Cfg::POS_PER_THREAD; ++j)
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+#if defined(CERB_X_NOGLDS)
+                    dst[cb][j][k] = __int_as_float(ta[j][k] + cb);
+#else
+                    dst[cb][j][k] = lds_f32(ta[j][k] + (uint32_t)(b * CB + cb) * kRawPlane);
+#endif
+                  }
+            };
+            if (ck_begin < ck_end) {
+              mbar_wait(&raw_full[rc], rcphase);
+              set_sources(rc);
+              load_batch(0, tv[0]);
+            }
+            for (int ck = ck_begin; ck < ck_end; ++ck) {
+              int rn = rc + 1;
+              uint32_t rnphase = rcphase;
+              if (rn == RS) { rn = 0; rnphase ^= 1; }
+#pragma unroll
+              for (int b = 0; b < NBAT; ++b) {
+                if (b + 1 < NBAT) {
+                  load_batch(b + 1, tv[(b + 1) & 1]);
+                } else if (ck + 1 < ck_end) {
+                  mbar_wait(&raw_full[rn], rnphase);
+                  set_sources(rn);
+                  load_batch(0, tv[0]);
+                }
+                if (b == 0) {
+                  mbar_wait(&empty_bar[stage], phase ^ 1);
+                  if (!a.use_tma_in) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
+                  const uint32_t dbase = dst0 + (uint32_t)stage * (uint32_t)(sizeof(float) * Cfg::X2_STAGE);
+#pragma unroll
+                  for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) da[j] = dbase + ((uint32_t)sdst[j] << 2);
+                  if (gt == 0 && ck < 4) CERB_TRACE(45 + 3 * ck);
+                }
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+                  for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+                    const float* v = tv[b & 1][cb][j];
+                    const float r = ((valid_mask >> j) & 1u) ? blend(v[0], v[1], v[2], v[3], taps[j]) : 0.f;
+                    sts_f32(da[j] + (uint32_t)(b * CB + cb) * kDstPlane, r);
+                  }
+              }
+              __syncwarp();
+              if (gt == 0 && ck < 4) CERB_TRACE(46 + 3 * ck);
+              if (lane == 0) mbar_arrive(&raw_empty[rc]);   // every tap of this chunk has been consumed by the blends above
+              rc = rn; rcphase = rnphase;
+              publish_stage();
+            }
+            ++titer;
+            continue;
+          }
           for (int ck = ck_begin; ck < ck_end; ++ck) {
+            if (lane == 0 && (ck == 2 || ck == 3)) CERB_TRACE(112 + (ck - 2) * 40 + gw * 6 + 0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (lane == 0 && (ck == 2 || ck == 3)) CERB_TRACE(112 + (ck - 2) * 40 + gw * 6 + 1);
             if (!a.use_tma_in && !raw16) coop_x1(x1s + stage * Cfg::X1_STAGE, ix0, iy0, ck * CC, n);
             if (gt == 0 && ck < 4) CERB_TRACE(44 + 3 * ck);
             mbar_wait(&raw_full[rc], rcphase);
+            if (lane == 0 && (ck == 2 || ck == 3)) CERB_TRACE(112 + (ck - 2) * 40 + gw * 6 + 2);
             if (gt == 0 && ck < 4) CERB_TRACE(45 + 3 * ck);
             const float* __restrict__ src = raws + rc * Cfg::RAW_STAGE;
             float* __restrict__ x2dst = x2s + stage * Cfg::X2_STAGE;
@@ -648,7 +787,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
                   for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
                     const float r = ((valid_mask >> j) & 1u) ? blend(tv16[j][0], tv16[j][1], tv16[j][2], tv16[j][3], taps[j]) : 0.f;
-                    if (sdst[j] >= 0) dp[sdst[j]] = r;
+                    dp[sdst[j]] = r;
                   }
                 }
                 __syncwarp();
@@ -658,24 +797,43 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
                 continue;
               }
             }
-            // Software pipeline over channel batches: the taps of batch b+1 are requested before
-            // batch b is blended and stored (the compiler cannot hoist shared loads above shared
-            // stores itself), so a warp never sits out a full LDS round trip per channel.
-            constexpr int CB = Cfg::POS_PER_THREAD >= 4 ? 1 : (Cfg::POS_PER_THREAD >= 2 ? 2 : 4);
+            // Lean gather: everything that does not change with the channel is in registers as a shared-memory
+            // byte address (tap sources, destination) -- per channel a tap is one LDS with an immediate offset,
+            // a sample 1 FMUL + 3 FFMA + 1 select + 1 STS.  (The plain indexed form cost ~40 instructions per
+            // sample, mostly address arithmetic and convergence barriers around predicated stores: the gather
+            // warps' instruction stream, not shared-memory bandwidth, was what the consumers waited for.)
+            // Software pipeline over channel batches: the taps of batch b+1 are requested before batch b is
+            // blended and stored (shared loads are not hoisted above shared stores).
+#ifdef CERB_AB_CB
+            constexpr int CB = Cfg::POS_PER_THREAD >= 4 ? CERB_AB_CB : (Cfg::POS_PER_THREAD >= 2 ? 2 : 4);
+#else
+            constexpr int CB = Cfg::POS_PER_THREAD >= 4 ? 2 : (Cfg::POS_PER_THREAD >= 2 ? 2 : 4);
+#endif
             constexpr int NBAT = CC / CB;
-            // (measured: helps the 4x16 configuration, -0.3 us; neutral to slightly negative for 8x32,
-            //  whose 16 loads per channel already cover the latency)
-            constexpr bool kPipe = CERB_AB_PIPE != 0 && CB > 1;
+            constexpr bool kPipe = CERB_AB_PIPE != 0 && NBAT > 1;
             static_assert(CC % CB == 0, "channel batches must divide the stage");
+            constexpr uint32_t kRawPlane = sizeof(float) * Cfg::RAW_H * Cfg::RAW_W;
+            constexpr uint32_t kDstPlane = sizeof(float) * Cfg::HY * Cfg::XS;
+            const uint32_t rbase = smem_u32(src), dbase = smem_u32(x2dst);
+            uint32_t ta[Cfg::POS_PER_THREAD][4], da[Cfg::POS_PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ta[j][k] = rbase + ((uint32_t)taps[j].off[k] << 2);  // off = 0 for invalid positions
+              da[j] = dbase + ((uint32_t)sdst[j] << 2);
+            }
             float tv[2][CB][Cfg::POS_PER_THREAD][4];
             auto load_batch = [&](int b, float (&dst)[CB][Cfg::POS_PER_THREAD][4]) {
 #pragma unroll
               for (int cb = 0; cb < CB; ++cb) {
-                const float* sp = src + (b * CB + cb) * (Cfg::RAW_H * Cfg::RAW_W);
 #pragma unroll
                 for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) dst[cb][j][k] = sp[taps[j].off[k]];  // off = 0 for invalid positions
+#if defined(CERB_X_NOGLDS) || defined(CERB_X_NOGATHER)
+                  for (int k = 0; k < 4; ++k) dst[cb][j][k] = __int_as_float(ta[j][k] + cb);
+#else
+                  for (int k = 0; k < 4; ++k) dst[cb][j][k] = lds_f32(ta[j][k] + (uint32_t)(b * CB + cb) * kRawPlane);
+#endif
                 }
               }
             };
@@ -686,16 +844,20 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
               else load_batch(b, tv[b & 1]);
 #pragma unroll
               for (int cb = 0; cb < CB; ++cb) {
-                float* dp = x2dst + (b * CB + cb) * (Cfg::HY * Cfg::XS);
 #pragma unroll
                 for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
                   const float* v = tv[b & 1][cb][j];
                   const float r = ((valid_mask >> j) & 1u) ? blend(v[0], v[1], v[2], v[3], taps[j]) : 0.f;
-                  if (sdst[j] >= 0) dp[sdst[j]] = r;
+#if defined(CERB_X_NOGATHER)
+                  if (r == 12345.678f) sts_f32(da[j] + (uint32_t)(b * CB + cb) * kDstPlane, r);
+#else
+                  sts_f32(da[j] + (uint32_t)(b * CB + cb) * kDstPlane, r);
+#endif
                 }
               }
             }
             __syncwarp();
+            if (lane == 0 && (ck == 2 || ck == 3)) CERB_TRACE(112 + (ck - 2) * 40 + gw * 6 + 3);
             if (gt == 0 && ck < 4) CERB_TRACE(46 + 3 * ck);
             if (lane == 0) mbar_arrive(&raw_empty[rc]);
             if (++rc == RS) { rc = 0; rcphase ^= 1; }
@@ -710,7 +872,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         // ahead across chunk boundaries -- only the shared-memory stores wait for a free stage.
         constexpr int NB = CC / kCBatch;
         constexpr int NV = Cfg::POS_PER_THREAD * kCBatch * 4;
-        const T* x2n = x2 + (long long)n * g.x2s[0];
+        const T* x2n = x2 + (long long)x2_item(g, n) * g.x2s[0];
         const int total_batches = (ck_end - ck_begin) * NB;
         const int gb0 = ck_begin * NB;
         float cur[NV], nxt[NV];
@@ -752,7 +914,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
               const float* v = &cur[(cb * Cfg::POS_PER_THREAD + j) * 4];
               const bool ok = ((valid_mask >> j) & 1u) && (ck * CC + bi * kCBatch + cb < g.C);
               const float r = !ok ? 0.f : (warped ? blend(v[0], v[1], v[2], v[3], taps[j]) : v[0]);
-              if (sdst[j] >= 0) plane_dst[sdst[j]] = r;
+              plane_dst[sdst[j]] = r;
             }
           }
           if (bi == NB - 1) publish_stage();
@@ -766,11 +928,23 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     }
   } else {
     // =========================== CONSUMER WARPS ===========================
-    const int grp = tid / Cfg::GROUP;
-    const int u = tid - grp * Cfg::GROUP;
-    const int strip = u / Cfg::COMBOS;
+    int grp, strip, combo;
+    if constexpr (Cfg::DIRECT_OUT && Cfg::NSTRIP == 4 && TY == 8) {
+      // lane = pair member | strip << 1 | pair-in-warp << 3: lanes (2k, 2k+1) are the two (y, dy) combos of a
+      // pair that reads the same x2 row (merged LDS.128), a quarter-warp is one pair x 4 strips (x1 rows y even /
+      // y odd -> disjoint swizzled chunks), and the 4 strips of a combo make the epilogue's stores contiguous
+      const int w = tid >> 5, l = tid & 31;
+      grp = 0;
+      strip = (l >> 1) & 3;
+      combo = w * 8 + (l >> 3) * 2 + (l & 1);
+    } else {
+      grp = tid / Cfg::GROUP;
+      const int u = tid - grp * Cfg::GROUP;
+      strip = u / Cfg::COMBOS;
+      combo = u - strip * Cfg::COMBOS;
+    }
     int y, dyi;
-    combo_of<TY>(u - strip * Cfg::COMBOS, y, dyi);
+    combo_of<TY>(combo, y, dyi);
     const float divisor = (float)g.C;  // k == 1: nelems = C (correlation_cuda_kernel.cu:85)
     const float rdivisor = __frcp_rn(divisor);
 
@@ -791,7 +965,13 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       for (int i = 0; i < 8 * kD; ++i) acc[i] = 0.f;
 
       for (int ck = ck_begin; ck < ck_end; ++ck) {
+#if defined(CERB_AB_CWAIT_HINT)
+        mbar_wait_hint(&full_bar[stage], phase, CERB_AB_CWAIT_HINT);
+#elif defined(CERB_AB_CWAIT_SLEEP)
+        mbar_wait_sleep(&full_bar[stage], phase, CERB_AB_CWAIT_SLEEP);
+#else
         mbar_wait(&full_bar[stage], phase);
+#endif
         if (tid == 0 && ck < 8) CERB_TRACE(17 + 2 * ck);
         const float* x1p = x1s + stage * Cfg::X1_STAGE;
         const float* x2p = x2s + stage * Cfg::X2_STAGE + x2_off;
@@ -799,6 +979,12 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         for (int cc = 0; cc < CC / KS; ++cc) {
           const int c = cc * KS + grp;
           float av[8], bv[16];
+#if defined(CERB_X_NOCLDS)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) av[i] = __int_as_float(0x3f800000 + i + c + ck);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) bv[i] = __int_as_float(0x3f800000 + 3 * i + c + ck);
+#else
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             int off = x1_off[h];
@@ -811,19 +997,59 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
             const float4 t = *reinterpret_cast<const float4*>(x2p + c * (Cfg::HY * Cfg::XS) + 4 * q);
             bv[4 * q + 0] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
           }
+#endif
+#if defined(CERB_X_NOFMA)
+#pragma unroll
+          for (int px = 0; px < 8; ++px) acc[px * kD] = fmaf(av[px], bv[px] + bv[px + 8], acc[px * kD]);
+#else
 #pragma unroll
           for (int px = 0; px < 8; ++px)
 #pragma unroll
             for (int dx = 0; dx < kD; ++dx) acc[px * kD + dx] = fmaf(av[px], bv[px + dx], acc[px * kD + dx]);
+#endif
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&empty_bar[stage]);
         if (tid == 0 && ck < 8) CERB_TRACE(18 + 2 * ck);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == Cfg::ST) { stage = 0; phase ^= 1; }
       }
       if (tid == 0) CERB_TRACE(40);
       if (tile + tile_step >= a.total_tiles) pdl_launch_dependents();  // last tile: only the epilogue is left
 
+      if constexpr (Cfg::DIRECT_OUT) {
+        // ---------------- epilogue: /C, LeakyReLU, straight to global memory ----------------
+        // A warp is 4 adjacent strips x 8 (y, dy) rows: every store instruction writes 8 output rows of
+        // 4 x 16 bytes, and a thread's two halves complete each 32-byte sector back to back.  No staged
+        // tile, no barrier: the consumers go back to the main loop as soon as the stores are issued.
+        const int oy = by0 + y, ox = bx0 + strip * 8;
+        if (oy < g.outH && ox < g.outW) {
+          T* op = (T*)a.out + (long long)n * g.os[0] + (long long)((un.woy + dyi) * g.D + un.wox) * g.os[1] +
+                  (long long)oy * g.os[2] + ox;
+          const bool vec = a.out_vec8 && ox + 8 <= g.outW;
+#pragma unroll
+          for (int dx = 0; dx < kD; ++dx) {
+            float v[8];
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+              float r = div_const(acc[px * kD + dx], divisor, rdivisor);
+              if (g.has_act) r = leaky(r, g.slope);
+              v[px] = r;
+            }
+#if defined(CERB_X_NOSTORE)
+            if (v[0] == 12345.678f)
+#endif
+            if (vec) {
+              store_row8<T>(op, v, a.out_vec8 > 1);
+            } else {
+              for (int px = 0; px < 8 && ox + px < g.outW; ++px) op[px] = from_f32<T>(v[px]);
+            }
+            op += g.os[1];
+          }
+        }
+        ++tiles_done;
+        ++titer;
+        continue;
+      }
       // ---------------- epilogue: /C, LeakyReLU, stage tile, TMA store ----------------
       const bool finalize_local = (KS == 1) || (S == 1);  // the cluster split is only used with KS > 1
       if (S == 1 && a.use_tma_out) {
@@ -999,7 +1225,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
       ++titer;
     }
     if (S == 1 && a.use_tma_out && (tid & 31) == 0 && (KS > 1 ? tid == 0 : tid < kD * 32)) tma_store_wait_read0();
-    if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 64 + 42] = clock64();
+    if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * kTraceSlots + 42] = clock64();
   }
 }
 
@@ -1022,7 +1248,7 @@ __global__ void __launch_bounds__(256) corr_fwd_generic_kernel(const Geom g, con
     const int n = (int)(t / g.D2);
     const int tj = tc / g.D - g.r, ti = tc % g.D - g.r;
     const T* x1n = x1 + (long long)n * g.x1s[0];
-    const T* x2n = x2 + (long long)n * g.x2s[0];
+    const T* x2n = x2 + (long long)x2_item(g, n) * g.x2s[0];
     float acc = 0.f;
     for (int j = -g.kr; j <= g.kr; ++j) {
       for (int i = -g.kr; i <= g.kr; ++i) {
@@ -1169,7 +1395,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
       a.use_tma_x2 = make_tmap_f32(&tm_x2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::XS, Cfg::HY, CC, false) ? 1 : 0;
     if ((tma_mask & 8) && warped_in)
       a.use_tma_raw = make_tmap_f32(&tm_raw, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W, Cfg::RAW_H, CC, false) ? 1 : 0;
-    if (tma_mask & 2)
+    if (!Cfg::DIRECT_OUT && (tma_mask & 2))
       a.use_tma_out = (make_tmap_out5d(&tm_out, out, g, TX, TY, kD) &&
                        (KS > 1 || make_tmap_out5d(&tm_outc, out, g, TX, TY, 1))) ? 1 : 0;   // KS == 1 also stores per displacement column
   }
@@ -1184,8 +1410,13 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
       a.use_tma_raw = 1;
     }
   }
-  if (sizeof(T) == 2)
-    a.out_vec8 = (((uintptr_t)out & 15) == 0 && g.os[0] % 8 == 0 && g.os[1] % 8 == 0 && g.os[2] % 8 == 0) ? 1 : 0;
+  {
+    const int per16 = 16 / (int)sizeof(T);
+    if (sizeof(T) == 2 || Cfg::DIRECT_OUT)
+      a.out_vec8 = (((uintptr_t)out & 15) == 0 && g.os[0] % per16 == 0 && g.os[1] % per16 == 0 && g.os[2] % per16 == 0) ? 1 : 0;
+    if (a.out_vec8 && sizeof(T) == 4 && ((uintptr_t)out & 31) == 0 && g.os[0] % 8 == 0 && g.os[1] % 8 == 0 && g.os[2] % 8 == 0)
+      a.out_vec8 = 2;   // 32-byte aligned rows: 256-bit stores
+  }
   auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS, UP>;
   static bool attr_set = false;  // benign race: the attribute call is idempotent
   if (!attr_set) {
@@ -1248,10 +1479,10 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
     }
     if (uf != nullptr) {
       if (small) return launch_fast<T, 4, 16, 4, 8, 2, true>(g, x1, x2, flow, out, no_tma, true, stream, uf);
-      return launch_fast<T, 8, 32, 1, 4, 3, true>(g, x1, x2, flow, out, no_tma, false, stream, uf);
+      return launch_fast<T, 8, 32, 1, CERB_AB_CC1, CERB_AB_RS1, true>(g, x1, x2, flow, out, no_tma, false, stream, uf);
     }
     if (small) return launch_fast<T, 4, 16, 4, 8, 2, false>(g, x1, x2, flow, out, no_tma, true, stream, uf);
-    return launch_fast<T, 8, 32, 1, 4, 3, false>(g, x1, x2, flow, out, no_tma, false, stream, uf);
+    return launch_fast<T, 8, 32, 1, CERB_AB_CC1, CERB_AB_RS1, false>(g, x1, x2, flow, out, no_tma, false, stream, uf);
   }
   if (uf != nullptr) return cudaErrorNotSupported;   // the generic kernel has no fused up-sampling
   const long long total = (long long)g.B * g.D2 * g.outH * g.outW;

@@ -46,8 +46,12 @@ def _corr_output_shape(x_shape, pad_size, kernel_size, max_displacement, stride1
 def warp_corr_forward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor] = None, pad_size: int = 4,
                       kernel_size: int = 1, max_displacement: int = 4, stride1: int = 1, stride2: int = 1,
                       corr_multiply: int = 1, warp_mode: int = WARP_TORCH, leaky_slope: Optional[float] = None,
-                      out: Optional[torch.Tensor] = None, variant: int = VARIANT_AUTO) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, variant: int = VARIANT_AUTO, x2_roll: int = 0) -> torch.Tensor:
     """leaky_relu(correlation(x1, flow_warp(x2, flow))) in one kernel launch.
+
+    ``x2_roll``: batch item n of x1 / flow / out is paired with item ``(n + x2_roll) % B`` of x2.  With
+    ``x1 = x2 = features of cat([image1, image2])`` and ``x2_roll = B // 2`` one launch computes both flow
+    directions of the reference's ``consistency=True`` forward (pwcnet.py:108-113) without copying a feature map.
 
     ``flow=None`` skips the warp, ``leaky_slope=None`` skips the activation; with both off this is
     the reference's ``torch.ops.cerberus.correlation`` (correlation_cuda.cpp:3-26).
@@ -69,7 +73,7 @@ def warp_corr_forward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.T
     elif tuple(out.shape) != shape or out.dtype != x1.dtype or out.stride(3) != 1:
         raise CostVolumeError(f"out must be {shape} {x1.dtype} with unit W stride")
     p = make_params(x1, x2, flow, out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
-                    warp_mode, leaky_slope)
+                    warp_mode, leaky_slope, int(x2_roll))
     with device_guard(x1.device):
         rc = lib().cerb_warp_corr_forward_variant(ctypes.byref(p), ptr(x1), ptr(x2), ptr(flow), ptr(out), int(variant),
                                                   ctypes.c_void_p(current_stream_ptr(x1.device)))

@@ -75,7 +75,11 @@ typedef struct cerb_corr_params {
   int32_t warp_mode;     /* CERB_WARP_*; only read when a flow pointer is given */
   float leaky_slope;     /* LeakyReLU negative slope fused on the output (pwcnet_sfd.py:182);
                             NaN (or negative) = no activation */
-  int32_t reserved;      /* must be 0 */
+  int32_t x2_batch_roll; /* 0 <= roll < batch: item n of x1 / flow / out is paired with item (n + roll) mod batch
+                            of x2 (0 = the reference pairing).  With x1 = x2 = features of [image 1; image 2]
+                            (batch 2N) and roll = N, one launch computes both flow directions of the reference's
+                            consistency=True forward (nnet_models/pwcnet.py:108-113, cerberus.py:131-135) without
+                            copying or re-ordering a feature map. */
   int64_t x1_stride[4], x2_stride[4], flow_stride[4], out_stride[4]; /* elements; 0,0,0,0 = contiguous */
 } cerb_corr_params;
 
