@@ -89,9 +89,10 @@ constexpr int kGatherThreads = kGatherWarps * 32;
 #define CERB_AB_CC1 4
 #endif
 constexpr int kRawMargin = 6;  // flow variation (px) inside one halo tile the raw box absorbs
+constexpr int kRawMarginL = 13; // ... and the large box (8x32 tiles only)
 constexpr int kCBatch = 1;     // direct-gather fallback: channels per software-pipelined batch
 
-enum { PATH_TMA_X2 = 0, PATH_RAW = 1, PATH_DIRECT = 2 };
+enum { PATH_TMA_X2 = 0, PATH_RAW = 1, PATH_DIRECT = 2, PATH_RAWL = 3 };
 
 // TY x TX output tile, KS-way in-CTA channel split, CC channels per pipeline stage, RS raw-box stages
 template <int TY, int TX, int KS, int CC_, int RS_>
@@ -121,7 +122,13 @@ struct FwdCfg {
   static constexpr int RAW16_X1_BYTES = CC * TY * TX * 2;
   static constexpr int X1_STAGE = CC * TY * TX;       // floats
   static constexpr int X2_STAGE = CC * HY * XS;       // floats
-  static constexpr int RAW_STAGE = CC * RAW_H * RAW_W;  // floats
+  // second, larger raw box for tiles whose flow varies more than +-kRawMargin px (a x2 up-sampled decoder flow with
+  // sigma = 3 px does): +-kRawMarginL px.  Same stage buffer, its own tensor map; only those tiles pay the extra
+  // bytes.  The 8x32 configuration has the room since its output no longer passes through shared memory.
+  static constexpr bool BIGBOX = DIRECT_OUT && CC <= 4;
+  static constexpr int RAWL_H = BIGBOX ? HY + 2 * kRawMarginL + 2 : RAW_H;
+  static constexpr int RAWL_W = BIGBOX ? (HX + 2 * kRawMarginL + 2 + 3 + 3) / 4 * 4 : RAW_W;
+  static constexpr int RAW_STAGE = CC * (RAWL_H * RAWL_W > RAW_H * RAW_W ? RAWL_H * RAWL_W : RAW_H * RAW_W);  // floats
   static constexpr int OUT_TILE = kD2 * TY * TX;       // floats, one partial buffer
   static constexpr size_t SMEM_X1 = 0;
   static constexpr size_t SMEM_X2 = SMEM_X1 + sizeof(float) * ST * X1_STAGE;
@@ -205,6 +212,7 @@ struct FwdArgs {
   int use_tma_in;   // x1 tiles by TMA
   int use_tma_x2;   // un-warped x2 halo tiles by TMA (flow == null)
   int use_tma_raw;  // raw x2 source boxes by TMA, warp gathered from shared memory
+  int use_tma_rawL; // the large raw box is available too
   int use_tma_out;  // output tile by TMA store
   int raw16;        // 16-bit inputs: raw x2 box and x1 tile by TMA as 16-bit data, converted by the gather warps
   int out_vec8;     // output rows may be written with 16-byte stores (base and N/C/H strides 16-byte aligned)
@@ -268,7 +276,8 @@ __device__ __forceinline__ Unit decode_unit(const FwdArgs& a, int tile) {
 template <typename T, int TY, int TX, int KS, int CC, int RS, bool UP>
 __global__ void __launch_bounds__(FwdCfg<TY, TX, KS, CC, RS>::NTHREADS, 1)
 warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1, const __grid_constant__ CUtensorMap tm_x2,
-                     const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_out,
+                     const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_rawL,
+                     const __grid_constant__ CUtensorMap tm_out,
                      const __grid_constant__ CUtensorMap tm_outc) {
   using Cfg = FwdCfg<TY, TX, KS, CC, RS>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -303,6 +312,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
     if (a.use_tma_in) tma_prefetch_desc(&tm_x1);
     if (a.use_tma_x2) tma_prefetch_desc(&tm_x2);
     if (a.use_tma_raw) tma_prefetch_desc(&tm_raw);
+    if (a.use_tma_rawL) tma_prefetch_desc(&tm_rawL);
     if (a.use_tma_out) { tma_prefetch_desc(&tm_out); if (KS == 1) tma_prefetch_desc(&tm_outc); }
   }
   __syncthreads();
@@ -401,6 +411,15 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           oy = ymin;
           if (raw16) ox = xmin & ~7;
           if (xmin <= xmax && xmax - ox < (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W) && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+          else if (Cfg::BIGBOX && a.use_tma_rawL && xmin <= xmax && xmax - ox < Cfg::RAWL_W && ymax - oy < Cfg::RAWL_H) path = PATH_RAWL;
+        }
+        if (lane == 0 && path == PATH_RAWL) {
+          for (int ck = ck_begin; ck < ck_end; ++ck) {
+            mbar_wait(&raw_empty[ri], riphase ^ 1);
+            mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * CC * Cfg::RAWL_H * Cfg::RAWL_W));
+            tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_rawL, &raw_full[ri], ox, oy, ck * CC, x2_item(g, n));
+            if (++ri == RS) { ri = 0; riphase ^= 1; }
+          }
         }
         if (lane == 0 && path == PATH_RAW) {
           for (int ck = ck_begin; ck < ck_end; ++ck) {
@@ -413,7 +432,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
               tma_load_4d(rs, &tm_raw, &raw_full[ri], ox, oy, ck * CC, x2_item(g, n));
               tma_load_4d(rs + Cfg::RAW16_X1_OFF, &tm_x1, &raw_full[ri], ix0, iy0, ck * CC, n);
             } else {
-              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * Cfg::RAW_STAGE));
+              mbar_arrive_expect_tx(&raw_full[ri], (uint32_t)(sizeof(float) * CC * Cfg::RAW_H * Cfg::RAW_W));
               tma_load_4d(raws + ri * Cfg::RAW_STAGE, &tm_raw, &raw_full[ri], ox, oy, ck * CC, x2_item(g, n));
             }
             if (++ri == RS) { ri = 0; riphase ^= 1; }
@@ -645,13 +664,14 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           ox = raw16 ? (xmin & ~7) : (xmin & ~3);  // TMA box starts must be 16-byte aligned
           oy = ymin;
           if (xmin <= xmax && xmax - ox < (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W) && ymax - oy < Cfg::RAW_H) path = PATH_RAW;
+          else if (Cfg::BIGBOX && a.use_tma_rawL && xmin <= xmax && xmax - ox < Cfg::RAWL_W && ymax - oy < Cfg::RAWL_H) path = PATH_RAWL;
         }
 #pragma unroll
         for (int j = 0; j < Cfg::POS_PER_THREAD; ++j) {
           const int x0 = taps[j].off[0], x1c = taps[j].off[1], y0 = taps[j].off[2], y1c = taps[j].off[3];
           int r0, r1;
-          const int raw_w = raw16 ? Cfg::RAW_W16 : Cfg::RAW_W;
-          if (path == PATH_RAW) { r0 = (y0 - oy) * raw_w - ox; r1 = (y1c - oy) * raw_w - ox; }
+          const int raw_w = path == PATH_RAWL ? Cfg::RAWL_W : (raw16 ? Cfg::RAW_W16 : Cfg::RAW_W);
+          if (path == PATH_RAW || path == PATH_RAWL) { r0 = (y0 - oy) * raw_w - ox; r1 = (y1c - oy) * raw_w - ox; }
           else { r0 = (int)(y0 * g.x2s[2]); r1 = (int)(y1c * g.x2s[2]); }
           const bool ok = (valid_mask >> j) & 1u;  // positions without a sample read offset 0 (always inside the source)
           taps[j].off[0] = ok ? r0 + x0 : 0; taps[j].off[1] = ok ? r0 + x1c : 0;
@@ -659,24 +679,15 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
         }
         if (gt == 0) CERB_TRACE(1);
 
-        if (path == PATH_RAW) {
+        if (path == PATH_RAW || path == PATH_RAWL) {
           // ------------- warp gathered from the raw source box in shared memory -------------
           if constexpr (sizeof(T) == 4) {
-            // Lean, software-pipelined gather.  Everything that does not change with the channel sits in registers
-            // as a shared-memory byte address (tap sources, destination): per channel a tap is one LDS with an
-            // immediate offset, a sample 1 FMUL + 3 FFMA + 1 select + 1 STS.  (The plain indexed form cost ~40
-            // instructions per sample, mostly address arithmetic and convergence barriers around predicated stores.)
-            // Channel batches are double-buffered ACROSS chunks: the taps of the next batch -- the first batch of the
-            // next chunk included, behind its raw_full wait -- are requested before the current batch is blended
-            // and stored, so neither an LDS round trip nor the barrier hand-over sits between two batches.
-#ifdef CERB_AB_CB
-            constexpr int CB = CERB_AB_CB;
-#else
-            constexpr int CB = 1;   // one channel per batch: 16 taps in flight per thread; two channels per batch spilled (128-register cap) and measured 12 % slower
-#endif
+            constexpr int CB = 1;
             constexpr int NBAT = CC / CB;
             static_assert(CC % CB == 0 && NBAT % 2 == 0, "an even number of channel batches per stage");
-            constexpr uint32_t kRawPlane = sizeof(float) * Cfg::RAW_H * Cfg::RAW_W;
+            // channel-plane stride of the box in use (two box sizes): a runtime value, so the tap addresses advance by it
+            // per channel (16 adds) instead of sitting in immediates -- two unrolled copies of this loop spilled
+            const uint32_t raw_plane = (uint32_t)sizeof(float) * (uint32_t)((Cfg::BIGBOX && path == PATH_RAWL) ? Cfg::RAWL_H * Cfg::RAWL_W : Cfg::RAW_H * Cfg::RAW_W);
             constexpr uint32_t kDstPlane = sizeof(float) * Cfg::HY * Cfg::XS;
             const uint32_t raw0 = smem_u32(raws), dst0 = smem_u32(x2s);
             uint32_t ta[Cfg::POS_PER_THREAD][4], da[Cfg::POS_PER_THREAD];
@@ -686,20 +697,17 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
 #pragma unroll
               for (int j = 0; j < Cfg::POS_PER_THREAD; ++j)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ta[j][k] = rbase + ((uint32_t)taps[j].off[k] << 2);  // off = 0 for invalid positions
+                for (int k = 0; k < 4; ++k) ta[j][k] = rbase + ((uint32_t)taps[j].off[k] << 2);
             };
-            auto load_batch = [&](int b, float (&dst)[CB][Cfg::POS_PER_THREAD][4]) {
+            auto load_batch = [&](int, float (&dst)[CB][Cfg::POS_PER_THREAD][4]) {   // next CB channels of the current box
 #pragma unroll
               for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
                 for (int j = 0; j < Cfg::POS_PER_THREAD; ++j)
 #pragma unroll
                   for (int k = 0; k < 4; ++k) {
-#if defined(CERB_X_NOGLDS)
-                    dst[cb][j][k] = __int_as_float(ta[j][k] + cb);
-#else
-                    dst[cb][j][k] = lds_f32(ta[j][k] + (uint32_t)(b * CB + cb) * kRawPlane);
-#endif
+                    dst[cb][j][k] = lds_f32(ta[j][k]);
+                    ta[j][k] += raw_plane;
                   }
             };
             if (ck_begin < ck_end) {
@@ -739,13 +747,13 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
               }
               __syncwarp();
               if (gt == 0 && ck < 4) CERB_TRACE(46 + 3 * ck);
-              if (lane == 0) mbar_arrive(&raw_empty[rc]);   // every tap of this chunk has been consumed by the blends above
+              if (lane == 0) mbar_arrive(&raw_empty[rc]);
               rc = rn; rcphase = rnphase;
               publish_stage();
             }
             ++titer;
             continue;
-          }
+          } else {
           for (int ck = ck_begin; ck < ck_end; ++ck) {
             if (lane == 0 && (ck == 2 || ck == 3)) CERB_TRACE(112 + (ck - 2) * 40 + gw * 6 + 0);
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -865,6 +873,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           }
           ++titer;
           continue;
+          }   // 16-bit inputs
         }
 
         // ------------- fallback: gather straight from global memory (any dtype / alignment / flow) -------------
@@ -1340,13 +1349,44 @@ static bool make_tmap_out5d(CUtensorMap* tm, const void* base, const Geom& g, in
   return r == CUDA_SUCCESS;
 }
 
+// SM count of the current device (cached per device: one process may drive several GPUs)
 static int num_sms() {
-  static int n = []() {
-    int dev = 0, v = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v > 0 ? v : 148;
-  }();
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int v = 0;
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  if (v <= 0) v = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
+}
+
+template <typename T, int TY, int TX, int KS, int CC, int RS, bool UP>
+static const void* kern_for_query() { return (const void*)warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS, UP>; }
+
+// co-resident clusters of `csize` CTAs for this kernel on the current device (cached per kernel / size / device)
+static int max_active_clusters(const void* kern, int threads, size_t smem, int csize) {
+  struct Key { const void* k; int c, dev, val; };
+  static Key cache[64];
+  static int ncache = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < ncache; ++i)
+    if (cache[i].k == kern && cache[i].c == csize && cache[i].dev == dev) return cache[i].val;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * 148);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at;
+  at.id = cudaLaunchAttributeClusterDimension;
+  at.val.clusterDim.x = (unsigned)csize; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = num_sms() / csize; }
+  if (ncache < 64) cache[ncache++] = Key{kern, csize, dev, n};   // benign race: worst case the query repeats
   return n;
 }
 
@@ -1375,13 +1415,14 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   a.nchunks = (g.C + CC - 1) / CC;
   a.dbg = g_trace_buffer;
   a.dbg_iter = g_trace_iter;
-  CUtensorMap tm_x1, tm_x2, tm_raw, tm_out, tm_outc;
+  CUtensorMap tm_x1, tm_x2, tm_raw, tm_rawL, tm_out, tm_outc;
   memset(&tm_x1, 0, sizeof(tm_x1));
   memset(&tm_x2, 0, sizeof(tm_x2));
   memset(&tm_raw, 0, sizeof(tm_raw));
+  memset(&tm_rawL, 0, sizeof(tm_rawL));
   memset(&tm_out, 0, sizeof(tm_out));
   memset(&tm_outc, 0, sizeof(tm_outc));
-  a.use_tma_in = a.use_tma_x2 = a.use_tma_raw = a.use_tma_out = 0;
+  a.use_tma_in = a.use_tma_x2 = a.use_tma_raw = a.use_tma_rawL = a.use_tma_out = 0;
   int tma_mask = 15;  // debugging knob CERB_DEBUG_TMA: bit0 x1 loads, bit1 stores, bit2 plain x2 tiles, bit3 raw x2 boxes
   if (const char* e = getenv("CERB_DEBUG_TMA")) tma_mask = atoi(e);
   if (std::is_same<T, float>::value && !force_no_tma) {
@@ -1395,6 +1436,8 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
       a.use_tma_x2 = make_tmap_f32(&tm_x2, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::XS, Cfg::HY, CC, false) ? 1 : 0;
     if ((tma_mask & 8) && warped_in)
       a.use_tma_raw = make_tmap_f32(&tm_raw, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAW_W, Cfg::RAW_H, CC, false) ? 1 : 0;
+    if (Cfg::BIGBOX && a.use_tma_raw && !getenv("CERB_DEBUG_NO_BIGBOX"))
+      a.use_tma_rawL = make_tmap_f32(&tm_rawL, x2, g.W, g.H, g.C, g.B, g.x2s, Cfg::RAWL_W, Cfg::RAWL_H, CC, false) ? 1 : 0;
     if (!Cfg::DIRECT_OUT && (tma_mask & 2))
       a.use_tma_out = (make_tmap_out5d(&tm_out, out, g, TX, TY, kD) &&
                        (KS > 1 || make_tmap_out5d(&tm_outc, out, g, TX, TY, 1))) ? 1 : 0;   // KS == 1 also stores per displacement column
@@ -1418,17 +1461,26 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
       a.out_vec8 = 2;   // 32-byte aligned rows: 256-bit stores
   }
   auto kern = warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS, UP>;
-  static bool attr_set = false;  // benign race: the attribute call is idempotent
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+  // function attributes are per device: remember which devices have the > 48 KB opt-in (benign race: idempotent call)
+  static unsigned long long attr_devs = 0ull;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (bit == 0ull || !(attr_devs & bit)) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+      if (e != cudaSuccess) return e;
+      attr_devs |= bit;
+    }
   }
   // coarse pyramid levels have fewer tiles than SMs: split the channel chunks of each tile over a
   // thread-block cluster (partial tiles reduced through DSMEM in the epilogue)
   int S = 1;
   if (allow_csplit && TX < 32 && !getenv("CERB_DEBUG_NO_CSPLIT")) {
     while (S < 8 && a.total_tiles * (S * 2) <= num_sms() && a.nchunks >= S * 2 && (Cfg::OUT_TILE % (S * 2 * 4)) == 0) S *= 2;
+    // every cluster must be resident at once (one tile per cluster, no second wave): clusters are placed inside
+    // one GPC, and not every GPC holds two clusters of 8 -- 16 tiles x 8 CTAs ran as two waves (17 vs 8.5 us)
+    while (S > 1 && max_active_clusters(kern_for_query<T, TY, TX, KS, CC, RS, UP>(), Cfg::NTHREADS, Cfg::SMEM_BYTES, S) < a.total_tiles) S /= 2;
   }
   a.csplit = S;
   a.csplit_log2 = S == 8 ? 3 : S == 4 ? 2 : S == 2 ? 1 : 0;
@@ -1459,7 +1511,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_x1, tm_x2, tm_raw, tm_out, tm_outc);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_x1, tm_x2, tm_raw, tm_rawL, tm_out, tm_outc);
   if (le != cudaSuccess) return le;
   return cudaGetLastError();
 }
@@ -1471,17 +1523,28 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
   if (fast_ok) {
     const int no_tma = (variant == CERB_FWD_VARIANT_FAST_NOTMA || variant == CERB_FWD_VARIANT_SMALL_NOTMA) ? 1 : 0;
     bool small = variant == CERB_FWD_VARIANT_SMALL || variant == CERB_FWD_VARIANT_SMALL_NOTMA;
+    bool mid = variant == CERB_FWD_VARIANT_MID;
     if (variant == CERB_FWD_VARIANT_AUTO) {
-      // not enough 8x32 tiles to fill the GPU: 4x16 tiles with the channels split four ways in-CTA
+      // Tile shape by how many work units it gives the 148 SMs: 8x32 (least halo per pixel) when that fills 3/4 of
+      // the GPU; else 4x16 tiles with the channels split four ways in the CTA (and over a cluster) while they
+      // still fit one wave; else 8x16 if that fits one wave (4x16 would need two); else 8x32 after all.
       const long long nwin = (g.D - kD + 7) / 8 + 1;
-      const long long big_tiles = (long long)g.B * ((g.outW + 31) / 32) * ((g.outH + 7) / 8) * nwin * nwin;
-      small = big_tiles < (long long)num_sms() * 3 / 4;
+      const long long per_b = (long long)g.B * nwin * nwin;
+      const long long big_tiles = per_b * ((g.outW + 31) / 32) * ((g.outH + 7) / 8);
+      const long long mid_tiles = per_b * ((g.outW + 15) / 16) * ((g.outH + 7) / 8);
+      const long long small_tiles = per_b * ((g.outW + 15) / 16) * ((g.outH + 3) / 4);
+      const long long sms = num_sms();
+      if (big_tiles >= sms * 3 / 4) { /* 8x32 */ }
+      else if (small_tiles <= sms) small = true;
+      else if (mid_tiles <= sms) mid = true;
     }
     if (uf != nullptr) {
       if (small) return launch_fast<T, 4, 16, 4, 8, 2, true>(g, x1, x2, flow, out, no_tma, true, stream, uf);
+      if (mid) return launch_fast<T, 8, 16, 2, 4, 2, true>(g, x1, x2, flow, out, no_tma, true, stream, uf);
       return launch_fast<T, 8, 32, 1, CERB_AB_CC1, CERB_AB_RS1, true>(g, x1, x2, flow, out, no_tma, false, stream, uf);
     }
     if (small) return launch_fast<T, 4, 16, 4, 8, 2, false>(g, x1, x2, flow, out, no_tma, true, stream, uf);
+    if (mid) return launch_fast<T, 8, 16, 2, 4, 2, false>(g, x1, x2, flow, out, no_tma, true, stream, uf);
     return launch_fast<T, 8, 32, 1, CERB_AB_CC1, CERB_AB_RS1, false>(g, x1, x2, flow, out, no_tma, false, stream, uf);
   }
   if (uf != nullptr) return cudaErrorNotSupported;   // the generic kernel has no fused up-sampling

@@ -13,7 +13,8 @@ enum {
   CERB_FWD_VARIANT_FAST_NOTMA = 2,  // 8x32 tiles, LDG/STG staging
   CERB_FWD_VARIANT_SMALL = 3,       // 4x16 tiles, channels split 4-way inside the CTA
   CERB_FWD_VARIANT_SMALL_NOTMA = 4,
-  CERB_FWD_VARIANT_GENERIC = 5      // one thread per output element, any parameters
+  CERB_FWD_VARIANT_GENERIC = 5,     // one thread per output element, any parameters
+  CERB_FWD_VARIANT_MID = 6          // 8x16 tiles, channels split 2-way inside the CTA
 };
 
 namespace cerb {

@@ -16,6 +16,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--notime", action="store_true")
 ap.add_argument("--tag", default="")
 ap.add_argument("--cases", default="L4:1,L4:2,L4:8,L3:1,L3:2")
+ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--flows", default="iid,smooth")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
@@ -100,7 +101,7 @@ for case in a.cases.split(","):
 
         def run():
             for (x1, x2, fl, out) in sets:
-                ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out)
+                ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out, variant=a.variant)
         with torch.cuda.stream(st):
             run(); torch.cuda.synchronize()
             with torch.cuda.graph(gr, stream=st):
