@@ -43,6 +43,16 @@ class TrtTensorDesc(ctypes.Structure):
     _fields_ = [("dims", TrtDims), ("type", ctypes.c_int32), ("format", ctypes.c_int32), ("scale", ctypes.c_float)]
 
 
+class TrtDims64(ctypes.Structure):
+    """nvinfer1::Dims of TensorRT >= 10 (int64 extents)."""
+    _fields_ = [("nbDims", ctypes.c_int32), ("d", ctypes.c_int64 * 8)]
+
+
+class TrtTensorDesc64(ctypes.Structure):
+    """Layout of nvinfer1::PluginTensorDesc with TensorRT >= 10 dims."""
+    _fields_ = [("dims", TrtDims64), ("type", ctypes.c_int32), ("format", ctypes.c_int32), ("scale", ctypes.c_float)]
+
+
 class TrtCorrFields(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("pad_size", "kernel_size", "max_displacement", "stride1", "stride2", "corr_multiply")]
@@ -57,7 +67,7 @@ EXPORTS = [
     "cerb_trt_corr_default_fields", "cerb_trt_corr_serialization_size", "cerb_trt_corr_serialize",
     "cerb_trt_corr_deserialize", "cerb_trt_corr_output_dims", "cerb_trt_corr_supports_format",
     "cerb_trt_corr_workspace_size", "cerb_trt_corr_enqueue", "cerb_trt_corr_enqueue_i64",
-    "cerb_trt_warp_corr_enqueue",
+    "cerb_trt_warp_corr_enqueue", "cerb_measure_fma_peak",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -72,8 +82,8 @@ def lib() -> ctypes.CDLL:
     override = os.environ.get("CERB_LIB_OVERRIDE")  # kernel A/B experiments (tools/ab_variants.py): an alternative build
     if override:
         path = override
-    elif not os.path.exists(path):
-        path = _build.build_library()
+    else:
+        path = _build.build_library()   # no-op unless a source or header is newer than the library (or it is missing)
     L = ctypes.CDLL(path)
     vp, i32, f32p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p
     pp = ctypes.POINTER(CorrParams)
@@ -109,6 +119,11 @@ def lib() -> ctypes.CDLL:
     L.cerb_trt_corr_enqueue.argtypes = [fp, dp, dp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
     L.cerb_trt_warp_corr_enqueue.argtypes = [fp, i32, ctypes.c_float, dp, dp, ctypes.POINTER(vp), ctypes.POINTER(vp),
                                              vp, vp]
+    dp64 = ctypes.POINTER(TrtTensorDesc64)
+    L.cerb_trt_corr_enqueue_i64.argtypes = [fp, dp64, dp64, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+    L.cerb_measure_fma_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
+    L.cerb_debug_set_path_counters.argtypes = [vp]
+    L.cerb_debug_set_path_counters.restype = None
     if L.cerb_abi_version() != 1:
         raise RuntimeError("libcerberus_costvolume.so: ABI version mismatch")
     _lib = L

@@ -33,6 +33,22 @@ def _stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False, extra_flags: list[str] | None = None) -> str:
     if not force and not _stale():
         return LIB_PATH
+    # one builder at a time (torchrun starts every rank at once): the others wait on the lock and then find
+    # the library up to date; the link goes to a temporary name and is renamed into place atomically
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB_PATH
+            return _build_locked(verbose, extra_flags)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, extra_flags: list[str] | None) -> str:
+    print(f"[cerberusnet_b200] building {LIB_NAME} with nvcc (sm_100a) ...", file=sys.stderr, flush=True)
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
@@ -50,10 +66,12 @@ def build_library(force: bool = False, verbose: bool = False, extra_flags: list[
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [_nvcc(), "-shared", "-ccbin", ccbin, "-o", LIB_PATH, *objs, "-lcudart"]
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
+    cmd = [_nvcc(), "-shared", "-ccbin", ccbin, "-o", tmp, *objs, "-lcudart"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout[-4000:]}")
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

@@ -277,6 +277,14 @@ int cerb_warp_corr_forward_host(const cerb_corr_params* p, const void* h_x1, con
 // Debugging aid, not part of the public ABI: per-CTA clock64() trace of the fast forward kernel.
 CERB_API void cerb_debug_set_trace_buffer(void* dev_ptr) { cerb::set_trace_buffer((long long*)dev_ptr); }
 CERB_API void cerb_debug_set_trace_iter(int it) { cerb::set_trace_iter(it); }
+// dev_ptr: 4 x uint64 on the device, zeroed by the caller: tiles per staging path of the warped forward
+// ([1] small raw box, [3] large raw box, [2] direct-gather fallback); NULL switches counting off.
+CERB_API void cerb_debug_set_path_counters(void* dev_ptr) { cerb::set_path_counters((unsigned long long*)dev_ptr); }
+
+int cerb_measure_fma_peak(double* tflops, cerb_stream_t stream) {
+  if (!tflops) return CERB_EINVAL;
+  return (int)cerb::measure_fma_peak(tflops, (cudaStream_t)stream);
+}
 
 uint64_t cerb_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 

@@ -49,6 +49,7 @@ struct BwdArgs {
   int nwin;                // 9 x 9 displacement windows per axis (1 for max_displacement 4)
   int async_ok[2];         // fp32 and 16-byte alignment of s[] rows: stage the halo tiles with cp.async
   int vec4_ok[2];          // 16-bit and 8-byte alignment of s[] rows: stage the halo tiles with 4-element loads
+  int s_roll[2], g_roll[2]; // batch-item roll applied when reading s[] / writing gdst[] (x2_batch_roll when they are x2 / grad_x2 themselves)
 };
 
 // Register-tiled backward of the correlation.  Both gradients have the form
@@ -94,7 +95,8 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
   const int tid = threadIdx.x;
   const int n = blockIdx.z;
   const int iy0 = blockIdx.y * BT_Y, ix0 = blockIdx.x * BT_X;
-  const T* __restrict__ src = (const T*)a.s[WHICH] + (long long)n * a.s_ns[WHICH];
+  const int n_src = (n + a.s_roll[WHICH]) % g.B, n_dst = (n + a.g_roll[WHICH]) % g.B;
+  const T* __restrict__ src = (const T*)a.s[WHICH] + (long long)n_src * a.s_ns[WHICH];
   const long long src_cs = a.s_cs[WHICH], src_hs = a.s_hs[WHICH];
   const T* __restrict__ gout = (const T*)a.gout + (long long)n * g.os[0];
   const T* __restrict__ outp = a.out ? (const T*)a.out + (long long)n * g.os[0] : nullptr;
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
 
   const float inv_c = 1.0f / (float)g.C;
   const long long plane_elems = (long long)g.H * g.W;
-  T* gdst = (T*)a.gdst[WHICH] + (long long)n * g.C * plane_elems;
+  T* gdst = (T*)a.gdst[WHICH] + (long long)n_dst * g.C * plane_elems;
   const bool async_s = kF32 && a.async_ok[WHICH];
 
   for (int c0 = 0; c0 < g.C; c0 += BCH) {
@@ -378,7 +380,7 @@ __global__ void __launch_bounds__(256) corr_bwd_generic_kernel(const Geom g, con
                                                                const T* __restrict__ second, long long sec_ns,
                                                                long long sec_cs, long long sec_hs,
                                                                const T* __restrict__ gout, const T* __restrict__ outp,
-                                                               T* __restrict__ gx1, T* __restrict__ gsecond) {
+                                                               T* __restrict__ gx1, T* __restrict__ gsecond, int sec_roll) {
   const long long total = (long long)g.B * g.C * g.H * g.W;
   const float inv = 1.0f / (float)(g.k * g.k * g.C);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -390,7 +392,8 @@ __global__ void __launch_bounds__(256) corr_bwd_generic_kernel(const Geom g, con
     const int c = (int)(t % g.C);
     const int n = (int)(t / g.C);
     const T* x1p = x1 + (long long)n * g.x1s[0] + (long long)c * g.x1s[1];
-    const T* sp = second + (long long)n * sec_ns + (long long)c * sec_cs;
+    const int n2 = (n + sec_roll) % g.B;   // batch item of the second input paired with item n
+    const T* sp = second + (long long)n2 * sec_ns + (long long)c * sec_cs;
     const T* gop = gout + (long long)n * g.os[0];
     const T* op = outp ? outp + (long long)n * g.os[0] : nullptr;
     float a1 = 0.f, a2 = 0.f;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(256) corr_bwd_generic_kernel(const Geom g, con
       }
     }
     gx1[idx] = from_f32<T>(a1 * inv);
-    gsecond[idx] = from_f32<T>(a2 * inv);
+    gsecond[idx + (long long)(n2 - n) * g.C * g.H * g.W] = from_f32<T>(a2 * inv);
   }
 }
 
@@ -444,7 +447,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict__ img, long long in_ns, long long in_cs,
                                                             long long in_hs, const float* __restrict__ flow,
                                                             long long f_ns, long long f_cs, long long f_hs,
-                                                            T* __restrict__ out, int B, int C, int H, int W, int mode) {
+                                                            T* __restrict__ out, int B, int C, int H, int W, int mode,
+                                                            int roll) {
   const long long plane = (long long)H * W;
   const long long total = (long long)B * plane;
   const AxisConst ax = make_axis(W), ay = make_axis(H);
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(256) flow_warp_fwd_kernel(const T* __restrict_
     const float sx = sample_pos(x, __ldg(fp), ax, mode & 3, in_x, !(mode & 4));
     const float sy = sample_pos(y, __ldg(fp + f_cs), ay, mode & 3, in_y, !(mode & 4));
     const Taps tp = make_taps(sx, sy, H, W, in_hs);
-    const T* ip = img + (long long)n * in_ns;
+    const T* ip = img + (long long)((n + roll) % B) * in_ns;
     T* op = out + (long long)n * C * plane + rem;
     int c = 0;
     for (; c + 4 <= C; c += 4) {   // 16 independent tap loads in flight
@@ -488,7 +492,7 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
                                                             long long f_ns, long long f_cs, long long f_hs,
                                                             const T* __restrict__ gout, GT* __restrict__ gimg,
                                                             float* __restrict__ gflow, int B, int C, int H, int W,
-                                                            int mode) {
+                                                            int mode, int roll) {
   const long long plane = (long long)H * W;
   const long long total = (long long)B * plane;
   const AxisConst ax = make_axis(W), ay = make_axis(H);
@@ -507,7 +511,8 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
     const float wx1 = fx + 1.f - sx, wx0 = sx - fx, wy1 = fy + 1.f - sy, wy0 = sy - fy;
     const bool bx1 = (int)fx + 1 < W, by1 = (int)fy + 1 < H;
     float gix = 0.f, giy = 0.f;
-    const T* ip = img + (long long)n * in_ns;
+    const int n2 = (n + roll) % B;   // the image (and its gradient) live at the rolled batch item
+    const T* ip = img + (long long)n2 * in_ns;
     for (int c0 = 0; c0 < C; c0 += 4) {   // 4 channels per batch: 20 independent loads in flight
       float gv[4], v[4][4];
 #pragma unroll
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(256) flow_warp_bwd_kernel(const T* __restrict_
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         if (c0 + k < C) {
-          GT* gp = gimg + ((long long)n * C + c0 + k) * plane;
+          GT* gp = gimg + ((long long)n2 * C + c0 + k) * plane;
           if (to.w[0] != 0.f) atomic_add_t<GT>(gp + to.off[0], gv[k] * to.w[0]);
           if (to.w[1] != 0.f) atomic_add_t<GT>(gp + to.off[1], gv[k] * to.w[1]);
           if (to.w[2] != 0.f) atomic_add_t<GT>(gp + to.off[2], gv[k] * to.w[2]);
@@ -562,13 +567,17 @@ static cudaError_t launch_tiled_pair(BwdArgs& a, const Geom& g, cudaStream_t str
   using Cfg = BwdCfg<TYB>;
   a.tiles_y = (g.H + TYB - 1) / TYB;
   dim3 grid(a.tiles_x, a.tiles_y, g.B);
-  static bool attr_set = false;  // benign race: idempotent
-  if (!attr_set) {
+  // function attributes are per device (one process may drive several GPUs): remember which have the opt-in
+  static unsigned long long attr_devs = 0ull;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (bit == 0ull || !(attr_devs & bit)) {
     cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 0, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 1, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_devs |= bit;
   }
   corr_bwd_tiled_kernel<T, 0, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
   corr_bwd_tiled_kernel<T, 1, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
@@ -590,7 +599,7 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
       if (workspace == nullptr) return cudaErrorInvalidValue;
       flow_warp_fwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
           (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], warped, g.B, g.C, g.H, g.W,
-          g.warp_mode);
+          g.warp_mode, g.x2roll);
     }
     const long long cs = (long long)g.H * g.W, ns = (long long)g.C * cs;
     BwdArgs a;
@@ -603,6 +612,8 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     a.out = out; a.gout = gout;
     a.gdst[0] = gx1;
     a.gdst[1] = flow ? (void*)gwarped : gx2;
+    a.s_roll[0] = flow ? 0 : g.x2roll; a.s_roll[1] = 0;      // the warped workspace is already in x1's batch order
+    a.g_roll[0] = 0; a.g_roll[1] = flow ? 0 : g.x2roll;
     a.off = g.md - g.pad;
     a.nwin = (g.D - kDb + 7) / 8 + 1;
     for (int w = 0; w < 2; ++w)   // halo rows start at ix0 + window origin - md: 16-byte aligned only if md % 4 == 0
@@ -625,14 +636,14 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
         if (e != cudaSuccess) return e;
         flow_warp_bwd_kernel<T, float><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
             (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, acc32, gflow, g.B,
-            g.C, g.H, g.W, g.warp_mode);
+            g.C, g.H, g.W, g.warp_mode, g.x2roll);
         cvt_from_f32_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(acc32, (T*)gx2, in_elems);
       } else {
         e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
         if (e != cudaSuccess) return e;
         flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
             (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
-            g.C, g.H, g.W, g.warp_mode);
+            g.C, g.H, g.W, g.warp_mode, g.x2roll);
       }
     }
     count_launches(flow != nullptr ? (sizeof(T) == 2 ? 6 : 5) : 2);
@@ -641,7 +652,8 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
   // generic parameters
   if (flow == nullptr) {
     corr_bwd_generic_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(
-        g, (const T*)x1, (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], (const T*)gout, (const T*)out, (T*)gx1, (T*)gx2);
+        g, (const T*)x1, (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], (const T*)gout, (const T*)out, (T*)gx1, (T*)gx2,
+        g.x2roll);
     count_launches(1);
     return cudaGetLastError();
   }
@@ -650,15 +662,15 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
   T* gwarped = warped + in_elems;
   flow_warp_fwd_kernel<T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
       (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], warped, g.B, g.C, g.H, g.W,
-      g.warp_mode);
+      g.warp_mode, g.x2roll);
   corr_bwd_generic_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(
       g, (const T*)x1, warped, (long long)g.C * g.H * g.W, (long long)g.H * g.W, (long long)g.W, (const T*)gout,
-      (const T*)out, (T*)gx1, gwarped);
+      (const T*)out, (T*)gx1, gwarped, 0);
   e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
   if (e != cudaSuccess) return e;
   flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
       (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B, g.C,
-      g.H, g.W, g.warp_mode);
+      g.H, g.W, g.warp_mode, g.x2roll);
   count_launches(4);
   return cudaGetLastError();
 }
@@ -679,7 +691,7 @@ static cudaError_t warp_fwd_t(const void* image, const float* flow, void* out, i
                               cudaStream_t stream) {
   const long long cs = (long long)H * W;
   flow_warp_fwd_kernel<T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
-      (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (T*)out, B, C, H, W, mode);
+      (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (T*)out, B, C, H, W, mode, 0);
   count_launches(1);
   return cudaGetLastError();
 }
@@ -702,7 +714,7 @@ static cudaError_t warp_bwd_t(const void* image, const float* flow, const void* 
   const long long cs = (long long)H * W;
   flow_warp_bwd_kernel<T, T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
       (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (const T*)gout, (T*)gimage,
-      gflow, B, C, H, W, mode);
+      gflow, B, C, H, W, mode, 0);
   count_launches(2);
   return cudaGetLastError();
 }

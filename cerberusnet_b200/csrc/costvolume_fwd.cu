@@ -45,6 +45,8 @@ static long long* g_trace_buffer = nullptr;  // debugging only
 void set_trace_buffer(long long* p) { g_trace_buffer = p; }
 long long* get_trace_buffer() { return g_trace_buffer; }
 static int g_trace_iter = 0;
+static unsigned long long* g_path_counters = nullptr;  // optional: tiles per staging path (bench.py reports the fallback rate)
+void set_path_counters(unsigned long long* p) { g_path_counters = p; }
 void set_trace_iter(int it) { g_trace_iter = it; }
 // records only the `dbg_iter`-th tile processed by each CTA (every role keeps its own `titer`)
 constexpr int kTraceSlots = 192;  // clock64 slots per CTA in the debugging trace
@@ -226,7 +228,8 @@ struct FwdArgs {
   int csplit_log2;
   int csplit;       // CTAs per cluster sharing one tile, each taking a slice of the channel chunks (1 = off)
   int dbg_iter;
-  long long* dbg;   // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 64 slots per CTA
+  long long* dbg;   // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer)
+  unsigned long long* path_ctr;   // optional: [PATH_*] tile counters of the warped gather (cerb_debug_set_path_counters)
 };
 
 // 16-byte chunk swizzle of a [rows][TX] fp32 tile: CU_TENSOR_MAP_SWIZZLE_128B for TX == 32
@@ -678,6 +681,7 @@ warp_corr_fwd_kernel(const FwdArgs a, const __grid_constant__ CUtensorMap tm_x1,
           taps[j].off[2] = ok ? r1 + x0 : 0; taps[j].off[3] = ok ? r1 + x1c : 0;
         }
         if (gt == 0) CERB_TRACE(1);
+        if (gt == 0 && a.path_ctr != nullptr) atomicAdd(&a.path_ctr[path], 1ull);
 
         if (path == PATH_RAW || path == PATH_RAWL) {
           // ------------- warp gathered from the raw source box in shared memory -------------
@@ -1414,6 +1418,7 @@ static cudaError_t launch_fast(const Geom& g, const void* x1, const void* x2, co
   a.total_tiles = g.B * a.tiles_x * a.tiles_y * a.nwin * a.nwin;
   a.nchunks = (g.C + CC - 1) / CC;
   a.dbg = g_trace_buffer;
+  a.path_ctr = g_path_counters;
   a.dbg_iter = g_trace_iter;
   CUtensorMap tm_x1, tm_x2, tm_raw, tm_rawL, tm_out, tm_outc;
   memset(&tm_x1, 0, sizeof(tm_x1));
@@ -1554,6 +1559,53 @@ static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, c
   if (blocks > cap) blocks = cap;
   corr_fwd_generic_kernel<T><<<(int)blocks, 256, 0, stream>>>(g, (const T*)x1, (const T*)x2, flow, (T*)out);
   return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ FMA roof --------------
+// 8 independent packed-FMA chains per thread (fma.rn.f32x2: two FMAs per lane per instruction), 1024 threads per SM.
+__global__ void __launch_bounds__(1024) fma_peak_kernel(float* out, int iters) {
+  unsigned long long a[8];
+  const unsigned long long m = 0x3f8000013f800001ull, c = 0x3a83126f3a83126full;   // {1.0000001, 1.0000001}, {0.001, 0.001}
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0x3f8000003f800000ull + (unsigned long long)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(m), "l"(c));
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s ^= a[i];
+  if (s == 0x1234567812345678ull) out[0] = 1.f;
+}
+
+cudaError_t measure_fma_peak(double* tflops, cudaStream_t stream) {
+  float* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, sizeof(float));
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = num_sms() * 2, iters = 20000;
+  fma_peak_kernel<<<blocks, 1024, 0, stream>>>(d, 2000);   // warm-up (clocks)
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, stream);
+    fma_peak_kernel<<<blocks, 1024, 0, stream>>>(d, iters);
+    cudaEventRecord(e1, stream);
+    e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = (double)blocks * 1024.0 * (double)iters * 32.0 * 2.0 * 2.0;   // 32 f32x2 FMAs per iteration
+    if (ms > 0.f) best = best > flops / (ms * 1e-3) / 1e12 ? best : flops / (ms * 1e-3) / 1e12;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e == cudaSuccess) *tflops = best;
+  return e;
 }
 
 cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,

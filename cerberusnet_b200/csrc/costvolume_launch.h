@@ -45,5 +45,9 @@ cudaError_t launch_flow_warp_backward(int dtype, const void* image, const float*
 void count_launches(int n);
 void set_trace_buffer(long long* p);
 void set_trace_iter(int it);
+void set_path_counters(unsigned long long* p);
+
+// fp32 FMA throughput of the current device (TFLOP/s), measured with a dependency-free FFMA2 loop over every SM
+cudaError_t measure_fma_peak(double* tflops, cudaStream_t stream);
 
 }  // namespace cerb

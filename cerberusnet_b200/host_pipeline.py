@@ -21,10 +21,14 @@ LevelShape = Tuple[int, int, int, bool]  # (C, H, W, warped)
 class HostPipeline:
     def __init__(self, levels: Sequence[LevelShape], batch: int = 1, depth: int = 2, device=None, pad_size: int = 4,
                  max_displacement: int = 4, warp_mode: int = WARP_TORCH, leaky_slope: Optional[float] = 0.1,
-                 dtype: torch.dtype = torch.float32):
+                 dtype: torch.dtype = torch.float32, x2_roll: int = 0, shared_features: bool = False):
+        """``shared_features`` with ``x2_roll = batch // 2``: each level takes ONE feature tensor holding
+        [features of image 1; features of image 2] that serves as both correlation inputs -- both flow
+        directions per launch, and every feature map crosses PCIe once instead of twice."""
         self.device = torch.device(device if device is not None else "cuda")
         self.levels, self.batch, self.depth = list(levels), batch, depth
         self.cfg = (pad_size, 1, max_displacement, 1, 1, 1, warp_mode, leaky_slope)
+        self.x2_roll, self.shared = int(x2_roll), bool(shared_features)
         d2 = (2 * max_displacement + 1) ** 2
         self.slots = []
         for _ in range(depth):
@@ -32,7 +36,7 @@ class HostPipeline:
             for (C, H, W, warped) in self.levels:
                 oh, ow = H + 2 * pad_size - 2 * max_displacement, W + 2 * pad_size - 2 * max_displacement
                 bufs.append((torch.empty(batch, C, H, W, dtype=dtype, device=self.device),
-                             torch.empty(batch, C, H, W, dtype=dtype, device=self.device),
+                             None if self.shared else torch.empty(batch, C, H, W, dtype=dtype, device=self.device),
                              torch.empty(batch, 2, H, W, dtype=torch.float32, device=self.device) if warped else None,
                              torch.empty(batch, d2, oh, ow, dtype=dtype, device=self.device)))
             self.slots.append(bufs)
@@ -44,9 +48,7 @@ class HostPipeline:
         self.ev_cmp = [torch.cuda.Event() for _ in range(depth)]
         self.ev_out = [torch.cuda.Event() for _ in range(depth)]
         self._n = 0
-        self.h2d_bytes = sum(b * t.element_size() for bufs in self.slots[:1] for lv in bufs
-                             for t, b in ((lv[0], lv[0].numel()), (lv[1], lv[1].numel())) ) + \
-            sum(lv[2].numel() * 4 for lv in self.slots[0] if lv[2] is not None)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for lv in self.slots[0] for t in lv[:3] if t is not None)
         self.d2h_bytes = sum(lv[3].numel() * lv[3].element_size() for lv in self.slots[0])
 
     def submit(self, host_in: Sequence[Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]],
@@ -56,23 +58,20 @@ class HostPipeline:
         reading `host_out`."""
         k = self._n % self.depth
         bufs = self.slots[k]
-        first_use = self._n < self.depth
+        # (waiting on an event that was never recorded is a no-op, so the first uses of a slot need no special case)
         with torch.cuda.stream(self.s_in):
-            if not first_use:
-                self.s_in.wait_event(self.ev_cmp[k])   # the kernels that last read this slot's inputs are done
+            self.s_in.wait_event(self.ev_cmp[k])   # the kernels that last read this slot's inputs are done
             for (d1, d2_, dfl, _), (h1, h2, hfl) in zip(bufs, host_in):
                 d1.copy_(h1, non_blocking=True)
-                d2_.copy_(h2, non_blocking=True)
+                if d2_ is not None:
+                    d2_.copy_(h2, non_blocking=True)
                 if dfl is not None:
                     dfl.copy_(hfl, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(self.ev_in[k])
-            if not first_use:
-                self.s_cmp.wait_event(self.ev_out[k])  # the previous result of this slot has left the device
-            pad, ks, md, s1, s2, mult, mode, slope = self.cfg
-            for (d1, d2_, dfl, dout) in bufs:
-                ops.warp_corr_forward(d1, d2_, dfl, pad, ks, md, s1, s2, mult, mode, slope, out=dout)
+            self.s_cmp.wait_event(self.ev_out[k])  # the previous result of this slot has left the device
+            self._launch(bufs)
             self.ev_cmp[k].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_cmp[k])
@@ -80,6 +79,12 @@ class HostPipeline:
                 hout.copy_(dout, non_blocking=True)
             self.ev_out[k].record(self.s_out)
         self._n += 1
+
+    def _launch(self, bufs) -> None:
+        pad, ks, md, s1, s2, mult, mode, slope = self.cfg
+        for (d1, d2_, dfl, dout) in bufs:
+            ops.warp_corr_forward(d1, d1 if d2_ is None else d2_, dfl, pad, ks, md, s1, s2, mult, mode, slope, out=dout,
+                                  x2_roll=self.x2_roll)
 
     # ---------------------------------------------------------------- packed arenas
     def enable_arenas(self) -> None:
@@ -93,8 +98,7 @@ class HostPipeline:
         dtype = self.slots[0][0][0].dtype
         if dtype != torch.float32:
             raise NotImplementedError("arenas are implemented for float32 staging")
-        n_in = sum(align(lv[0].numel()) + align(lv[1].numel()) + (align(lv[2].numel()) if lv[2] is not None else 0)
-                   for lv in self.slots[0])
+        n_in = sum(align(t.numel()) for lv in self.slots[0] for t in lv[:3] if t is not None)
         n_out = sum(align(lv[3].numel()) for lv in self.slots[0])
         self._arenas = []
         for k in range(self.depth):
@@ -132,19 +136,14 @@ class HostPipeline:
         D2H copy, on the three streams."""
         k = slot
         d_in, d_out, h_in, h_out, _, _ = self._arenas[k]
-        first_use = self._n < self.depth
         with torch.cuda.stream(self.s_in):
-            if not first_use:
-                self.s_in.wait_event(self.ev_cmp[k])
+            self.s_in.wait_event(self.ev_cmp[k])    # no-op until the slot has been used once
             d_in.copy_(h_in, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_cmp):
             self.s_cmp.wait_event(self.ev_in[k])
-            if not first_use:
-                self.s_cmp.wait_event(self.ev_out[k])
-            pad, ks, md, s1, s2, mult, mode, slope = self.cfg
-            for (d1, d2_, dfl, dout) in self.slots[k]:
-                ops.warp_corr_forward(d1, d2_, dfl, pad, ks, md, s1, s2, mult, mode, slope, out=dout)
+            self.s_cmp.wait_event(self.ev_out[k])
+            self._launch(self.slots[k])
             self.ev_cmp[k].record(self.s_cmp)
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.ev_cmp[k])

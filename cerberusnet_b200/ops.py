@@ -123,8 +123,9 @@ def warp_corr_forward_upflow(x1: torch.Tensor, x2: torch.Tensor, flow_coarse: to
 def warp_corr_backward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.Tensor], out: Optional[torch.Tensor],
                        grad_out: torch.Tensor, pad_size: int = 4, kernel_size: int = 1, max_displacement: int = 4,
                        stride1: int = 1, stride2: int = 1, corr_multiply: int = 1, warp_mode: int = WARP_TORCH,
-                       leaky_slope: Optional[float] = None):
-    """Gradients of :func:`warp_corr_forward`: ``(grad_x1, grad_x2, grad_flow or None)``."""
+                       leaky_slope: Optional[float] = None, x2_roll: int = 0):
+    """Gradients of :func:`warp_corr_forward`: ``(grad_x1, grad_x2, grad_flow or None)``.  With ``x2_roll`` the
+    second gradient is laid out like x2 itself (item ``(n + x2_roll) % B`` receives what item n's output sent back)."""
     require_cuda(x1, x2, flow, out, grad_out)
     x1, x2 = _inner_contig(x1), _inner_contig(x2)
     if flow is not None:
@@ -135,7 +136,7 @@ def warp_corr_backward(x1: torch.Tensor, x2: torch.Tensor, flow: Optional[torch.
     if leaky_slope is not None and out is None:
         raise CostVolumeError("the activated forward output is needed for the LeakyReLU backward")
     p = make_params(x1, x2, flow, grad_out, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply,
-                    warp_mode, leaky_slope)
+                    warp_mode, leaky_slope, int(x2_roll))
     g1 = torch.empty(x1.shape, dtype=x1.dtype, device=x1.device)
     g2 = torch.empty(x2.shape, dtype=x2.dtype, device=x2.device)
     gflow = torch.empty(flow.shape, dtype=torch.float32, device=x1.device) if flow is not None else None

@@ -164,6 +164,11 @@ CERB_API int cerb_warp_corr_forward_host(const cerb_corr_params* p, const void* 
                                          const float* h_flow, void* h_out, void* dev_workspace,
                                          size_t dev_workspace_bytes, cerb_stream_t stream);
 
+/* Measures the fp32 FMA throughput (TFLOP/s) of the current device with a dependency-free packed-FMA loop on every
+ * SM: the compute roof bench.py reports next to the HBM roof ("the harness must measure one").
+ * Synchronises `stream`; ~20 ms. */
+CERB_API int cerb_measure_fma_peak(double* tflops, cerb_stream_t stream);
+
 /* Number of SMs / kernel launches issued so far by this library in this process (the
  * `gpu_launches` claim in bench.py). */
 CERB_API uint64_t cerb_launch_count(void);
