@@ -8,7 +8,8 @@ the LeakyReLU(0.1) that follows it, behind the reference's own Python surfaces
 from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolumeError, lib  # noqa: F401
 from .correlation import (Correlation, CorrelationFunction, CorrelationTorch, UpflowWarpCorrelationFunction,  # noqa: F401
                           WarpCorrelation, WarpCorrelationFunction, warp_correlation, warp_correlation_upflow)
-from .flow_warp import FlowWarpFunction, flow_warp, mesh_grid, norm_grid  # noqa: F401
+from .flow_warp import FlowWarpFunction, flow_warp, grid_sample, mesh_grid, norm_grid  # noqa: F401
+from .photometric import PhotometricLossFunction, photometric_loss  # noqa: F401
 from .install import install, patch_flow_warp  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from . import ops  # noqa: F401

@@ -58,6 +58,14 @@ class TrtCorrFields(ctypes.Structure):
                 ("pad_size", "kernel_size", "max_displacement", "stride1", "stride2", "corr_multiply")]
 
 
+class TrtGridSamplerFields(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("align_corners", "interpolation_mode", "padding_mode")]
+
+
+class TrtWarpCorrFields(ctypes.Structure):
+    _fields_ = [("corr", TrtCorrFields), ("warp_mode", ctypes.c_int32), ("leaky_slope", ctypes.c_float)]
+
+
 EXPORTS = [
     "cerb_abi_version", "cerb_error_string", "cerb_corr_output_dims", "cerb_warp_corr_forward",
     "cerb_warp_corr_forward_variant", "cerb_warp_corr_forward_upflow", "cerb_warp_corr_backward_workspace",
@@ -67,7 +75,11 @@ EXPORTS = [
     "cerb_trt_corr_default_fields", "cerb_trt_corr_serialization_size", "cerb_trt_corr_serialize",
     "cerb_trt_corr_deserialize", "cerb_trt_corr_output_dims", "cerb_trt_corr_supports_format",
     "cerb_trt_corr_workspace_size", "cerb_trt_corr_enqueue", "cerb_trt_corr_enqueue_i64",
-    "cerb_trt_warp_corr_enqueue", "cerb_measure_fma_peak",
+    "cerb_trt_warp_corr_enqueue", "cerb_measure_fma_peak", "cerb_grid_sample_forward",
+    "cerb_trt_warp_corr_default_fields", "cerb_trt_warp_corr_serialize", "cerb_trt_warp_corr_deserialize",
+    "cerb_trt_grid_sampler_default_fields", "cerb_trt_grid_sampler_serialize", "cerb_trt_grid_sampler_deserialize",
+    "cerb_trt_grid_sampler_enqueue",
+    "cerb_photometric_workspace", "cerb_photometric_forward", "cerb_photometric_backward",
 ]
 
 _lib: Optional[ctypes.CDLL] = None
@@ -122,6 +134,24 @@ def lib() -> ctypes.CDLL:
     dp64 = ctypes.POINTER(TrtTensorDesc64)
     L.cerb_trt_corr_enqueue_i64.argtypes = [fp, dp64, dp64, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
     L.cerb_measure_fma_peak.argtypes = [ctypes.POINTER(ctypes.c_double), vp]
+    L.cerb_grid_sample_forward.argtypes = [vp, vp, vp] + [i32] * 11 + [vp]
+    L.cerb_photometric_workspace.argtypes = [i32, i32, i32]
+    L.cerb_photometric_workspace.restype = ctypes.c_size_t
+    L.cerb_photometric_forward.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, i32, vp]
+    L.cerb_photometric_backward.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, ctypes.c_float, ctypes.c_float, i32, vp]
+    gfp = ctypes.POINTER(TrtGridSamplerFields)
+    L.cerb_trt_grid_sampler_default_fields.argtypes = [gfp]
+    L.cerb_trt_grid_sampler_default_fields.restype = None
+    L.cerb_trt_grid_sampler_serialize.argtypes = [gfp, vp]
+    L.cerb_trt_grid_sampler_serialize.restype = ctypes.c_size_t
+    L.cerb_trt_grid_sampler_deserialize.argtypes = [vp, ctypes.c_size_t, gfp]
+    L.cerb_trt_grid_sampler_enqueue.argtypes = [gfp, dp, dp, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+    wfp = ctypes.POINTER(TrtWarpCorrFields)
+    L.cerb_trt_warp_corr_default_fields.argtypes = [wfp]
+    L.cerb_trt_warp_corr_default_fields.restype = None
+    L.cerb_trt_warp_corr_serialize.argtypes = [wfp, vp]
+    L.cerb_trt_warp_corr_serialize.restype = ctypes.c_size_t
+    L.cerb_trt_warp_corr_deserialize.argtypes = [vp, ctypes.c_size_t, wfp]
     L.cerb_debug_set_path_counters.argtypes = [vp]
     L.cerb_debug_set_path_counters.restype = None
     if L.cerb_abi_version() != 1:

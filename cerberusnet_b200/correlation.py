@@ -100,7 +100,9 @@ class Correlation(torch.nn.Module):
         self.corr_multiply = corr_multiply
 
     def forward(self, input1, input2):
-        if self.training:
+        # the reference uses the autograd Function only in training mode (correlation.py:72-80), which silently cuts the
+        # graph when a frozen-BN fine-tune runs the module in eval(): keep the graph whenever a gradient is wanted
+        if self.training or (torch.is_grad_enabled() and (input1.requires_grad or input2.requires_grad)):
             return CorrelationFunction.apply(input1, input2, self.pad_size, self.kernel_size, self.max_displacement,
                                              self.stride1, self.stride2, self.corr_multiply)
         return ops.warp_corr_forward(input1, input2, None, self.pad_size, self.kernel_size, self.max_displacement,

@@ -228,6 +228,54 @@ int cerb_flow_warp_backward(const void* image, const float* flow, const void* gr
                                         width, warp_mode, (cudaStream_t)stream);
 }
 
+int cerb_grid_sample_forward(const void* input, const void* grid, void* output, int32_t batch, int32_t channels,
+                             int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t dtype,
+                             int32_t interpolation_mode, int32_t padding_mode, int32_t align_corners, int32_t convention,
+                             cerb_stream_t stream) {
+  if (!input || !grid || !output || batch < 1 || channels < 1 || in_h < 1 || in_w < 1 || out_h < 1 || out_w < 1)
+    return CERB_EINVAL;
+  if (dtype != CERB_F32 && dtype != CERB_F16 && dtype != CERB_BF16) return CERB_EINVAL;
+  if (interpolation_mode != CERB_GRID_BILINEAR && interpolation_mode != CERB_GRID_NEAREST) return CERB_EUNSUPPORTED;
+  if (padding_mode < CERB_GRID_PAD_ZEROS || padding_mode > CERB_GRID_PAD_REFLECTION) return CERB_EINVAL;
+  if (convention != CERB_GRID_CONV_TRT && convention != CERB_GRID_CONV_ATEN) return CERB_EINVAL;
+  if ((long long)in_h * in_w >= 0x7fffffffLL) return CERB_ESTRIDE;
+  return (int)launch_grid_sampler(dtype, input, grid, output, batch, channels, in_h, in_w, out_h, out_w, interpolation_mode,
+                                  padding_mode, align_corners ? 1 : 0, convention, (cudaStream_t)stream);
+}
+
+size_t cerb_photometric_workspace(int32_t batch, int32_t height, int32_t width) {
+  if (batch < 1 || height < 1 || width < 1) return 0;
+  return photometric_workspace_bytes(batch, height, width);
+}
+
+static int photometric_args_ok(int32_t batch, int32_t channels, int32_t height, int32_t width, int32_t warp_mode) {
+  if (batch < 1 || channels < 1 || height < 4 || width < 4) return CERB_EINVAL;   // ReflectionPad2d(1) + one mirror per axis
+  if (warp_mode < CERB_WARP_TORCH || warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
+  if ((long long)channels * height * width >= 0x7fffffffLL) return CERB_ESTRIDE;
+  return CERB_OK;
+}
+
+int cerb_photometric_forward(const float* im_orig, const float* im_src, const float* flow, float* loss, void* workspace,
+                             size_t workspace_bytes, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                             float l1_weight, float ssim_weight, int32_t warp_mode, cerb_stream_t stream) {
+  if (!im_orig || !im_src || !flow || !loss || !workspace) return CERB_EINVAL;
+  const int rc = photometric_args_ok(batch, channels, height, width, warp_mode);
+  if (rc != CERB_OK) return rc;
+  if (workspace_bytes < cerb_photometric_workspace(batch, height, width)) return CERB_EWORKSPACE;
+  return (int)launch_photometric_forward(im_orig, im_src, flow, loss, workspace, batch, channels, height, width, l1_weight,
+                                         ssim_weight, warp_mode, (cudaStream_t)stream);
+}
+
+int cerb_photometric_backward(const float* im_orig, const float* im_src, const float* flow, const float* grad_loss,
+                              float* grad_flow, int32_t batch, int32_t channels, int32_t height, int32_t width,
+                              float l1_weight, float ssim_weight, int32_t warp_mode, cerb_stream_t stream) {
+  if (!im_orig || !im_src || !flow || !grad_loss || !grad_flow) return CERB_EINVAL;
+  const int rc = photometric_args_ok(batch, channels, height, width, warp_mode);
+  if (rc != CERB_OK) return rc;
+  return (int)launch_photometric_backward(im_orig, im_src, flow, grad_loss, grad_flow, batch, channels, height, width,
+                                          l1_weight, ssim_weight, warp_mode, (cudaStream_t)stream);
+}
+
 // ---------------------------------------------------------------- host-buffer end-to-end ---
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -357,6 +405,69 @@ int cerb_trt_warp_corr_enqueue(const cerb_trt_corr_fields* f, int32_t warp_mode,
                                cerb_stream_t stream) {
   if (warp_mode < CERB_WARP_TORCH || warp_mode > CERB_WARP_TORCH_CPU) return CERB_EINVAL;
   return trt_enqueue_impl(f, warp_mode, leaky_slope, true, input_desc, output_desc, inputs, outputs, stream);
+}
+
+void cerb_trt_warp_corr_default_fields(cerb_trt_warp_corr_fields* f) {
+  if (!f) return;
+  cerb_trt_corr_default_fields(&f->corr);
+  f->warp_mode = CERB_WARP_TRT;
+  f->leaky_slope = 0.1f;
+}
+
+size_t cerb_trt_warp_corr_serialize(const cerb_trt_warp_corr_fields* f, void* buffer) {
+  if (!buffer) return sizeof(cerb_trt_warp_corr_fields);
+  if (!f) return 0;
+  memcpy(buffer, f, sizeof(*f));   // six int32, int32 warp_mode, float slope
+  return sizeof(*f);
+}
+
+int cerb_trt_warp_corr_deserialize(const void* data, size_t length, cerb_trt_warp_corr_fields* f) {
+  if (!data || !f || length != sizeof(*f)) return CERB_EINVAL;
+  memcpy(f, data, sizeof(*f));
+  return CERB_OK;
+}
+
+void cerb_trt_grid_sampler_default_fields(cerb_trt_grid_sampler_fields* f) {
+  if (!f) return;
+  f->align_corners = 0; f->interpolation_mode = CERB_GRID_BILINEAR; f->padding_mode = CERB_GRID_PAD_BORDER;   // grid_sampler.cpp:40-42
+}
+
+size_t cerb_trt_grid_sampler_serialize(const cerb_trt_grid_sampler_fields* f, void* buffer) {
+  const size_t n = 1 + 2 * sizeof(int32_t);   // bool, int, int (grid_sampler.cpp:57-74)
+  if (!buffer) return n;
+  if (!f) return 0;
+  unsigned char* d = (unsigned char*)buffer;
+  d[0] = f->align_corners ? 1 : 0;
+  memcpy(d + 1, &f->interpolation_mode, 4);
+  memcpy(d + 5, &f->padding_mode, 4);
+  return n;
+}
+
+int cerb_trt_grid_sampler_deserialize(const void* data, size_t length, cerb_trt_grid_sampler_fields* f) {
+  if (!data || !f || length != 9) return CERB_EINVAL;
+  const unsigned char* d = (const unsigned char*)data;
+  f->align_corners = d[0] ? 1 : 0;
+  memcpy(&f->interpolation_mode, d + 1, 4);
+  memcpy(&f->padding_mode, d + 5, 4);
+  return CERB_OK;
+}
+
+int cerb_trt_grid_sampler_enqueue(const cerb_trt_grid_sampler_fields* f, const cerb_trt_tensor_desc* in,
+                                  const cerb_trt_tensor_desc* out, const void* const* inputs, void* const* outputs,
+                                  void* /*workspace*/, cerb_stream_t stream) {
+  if (!f || !in || !out || !inputs || !outputs) return CERB_EINVAL;
+  if (in[0].dims.nbDims != 4 || in[1].dims.nbDims != 4 || out[0].dims.nbDims != 4 || in[1].dims.d[3] != 2) return CERB_EINVAL;
+  if (in[0].type != in[1].type || out[0].type != in[0].type) return CERB_EUNSUPPORTED;
+  int dtype;
+  if (in[0].type == CERB_TRT_FLOAT) dtype = CERB_F32;
+  else if (in[0].type == CERB_TRT_HALF) dtype = CERB_F16;
+  else return CERB_EUNSUPPORTED;   // reference throws (grid_sampler.cu:263-266)
+  if (out[0].dims.d[0] != in[0].dims.d[0] || out[0].dims.d[1] != in[0].dims.d[1] || out[0].dims.d[2] != in[1].dims.d[1] ||
+      out[0].dims.d[3] != in[1].dims.d[2] || in[1].dims.d[0] != in[0].dims.d[0])
+    return CERB_ESHAPE;
+  return cerb_grid_sample_forward(inputs[0], inputs[1], outputs[0], in[0].dims.d[0], in[0].dims.d[1], in[0].dims.d[2],
+                                  in[0].dims.d[3], out[0].dims.d[2], out[0].dims.d[3], dtype, f->interpolation_mode,
+                                  f->padding_mode, f->align_corners, CERB_GRID_CONV_TRT, stream);
 }
 
 }  // extern "C"

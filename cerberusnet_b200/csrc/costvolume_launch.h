@@ -42,6 +42,15 @@ cudaError_t launch_flow_warp_forward(int dtype, const void* image, const float* 
 cudaError_t launch_flow_warp_backward(int dtype, const void* image, const float* flow, const void* gout, void* gimage,
                                       float* gflow, int B, int C, int H, int W, int mode, cudaStream_t stream);
 
+cudaError_t launch_grid_sampler(int dtype, const void* input, const void* grid, void* out, int N, int C, int H, int W, int oH,
+                                int oW, int interp, int padding, int align, int conv, cudaStream_t stream);
+
+size_t photometric_workspace_bytes(int B, int H, int W);
+cudaError_t launch_photometric_forward(const float* orig, const float* src, const float* flow, float* loss, void* workspace, int B,
+                                       int C, int H, int W, float l1_w, float ssim_w, int mode, cudaStream_t stream);
+cudaError_t launch_photometric_backward(const float* orig, const float* src, const float* flow, const float* gloss, float* gflow,
+                                        int B, int C, int H, int W, float l1_w, float ssim_w, int mode, cudaStream_t stream);
+
 void count_launches(int n);
 void set_trace_buffer(long long* p);
 void set_trace_iter(int it);

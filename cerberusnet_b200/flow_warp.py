@@ -11,7 +11,7 @@ import torch
 from . import ops
 from ._lib import WARP_TORCH, WARP_TORCH_CPU, WARP_TRT
 
-__all__ = ["flow_warp", "FlowWarpFunction", "mesh_grid", "norm_grid"]
+__all__ = ["flow_warp", "FlowWarpFunction", "mesh_grid", "norm_grid", "grid_sample"]
 
 
 class FlowWarpFunction(torch.autograd.Function):
@@ -62,3 +62,11 @@ def norm_grid(v_grid: torch.Tensor) -> torch.Tensor:
     gx = 2.0 * v_grid[:, 0] / (width - 1) - 1.0
     gy = 2.0 * v_grid[:, 1] / (height - 1) - 1.0
     return torch.stack([gx, gy], dim=-1)
+
+
+def grid_sample(input: torch.Tensor, grid: torch.Tensor, mode: str = "bilinear", padding_mode: str = "zeros",
+                align_corners: bool = False, convention: str = "aten") -> torch.Tensor:
+    """``F.grid_sample`` signature on the CUDA kernel behind the reference's TensorRT grid-sampler plugin
+    (trt_plugins/grid_sampler.cu); ``convention='trt'`` reproduces the plugin's own un-normalise.  Forward only
+    (the plugin is an inference node); training code warps through :func:`flow_warp`."""
+    return ops.grid_sample_forward(input, grid, mode, padding_mode, align_corners, convention)

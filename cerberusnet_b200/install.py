@@ -8,8 +8,10 @@ The reference models bind the hot path by module path and by name:
 ``install()`` registers :mod:`cerberusnet_b200.correlation` in ``sys.modules`` under the
 reference's dotted name *before* the models are imported (the reference module itself cannot be
 imported: its line 2 loads a py3.8 .so by a cwd-relative path), and ``patch_flow_warp()`` swaps
-the ``flow_warp`` name inside already-imported model modules.  ``fuse_decoder()`` goes one step
-further and replaces the three-op sequence of a PWC-style head by the fused kernel.
+the ``flow_warp`` name inside already-imported model modules -- the reference's loss module
+(``nnet_training.loss_functions.UnFlowLoss``, whose ``unFlowLoss.forward`` warps the image pyramid at four scales in
+both directions, UnFlowLoss.py:279-283) included.  The fused forms (``WarpCorrelation``, ``decoder.FlowDecoder``,
+``photometric.photometric_loss``) are opt-in replacements for callers that adopt them.
 """
 from __future__ import annotations
 
@@ -29,6 +31,9 @@ REFERENCE_MODEL_MODULES = (
     "nnet_training.nnet_models.ocrnet_sfd",
     "nnet_training.nnet_models.detr_sfd",
 )
+# the loss side binds flow_warp inside its own module (UnFlowLoss.py:83, used at :279-283): patching the module's
+# global redirects every call unFlowLoss.forward makes
+REFERENCE_LOSS_MODULES = ("nnet_training.loss_functions.UnFlowLoss",)
 
 
 def install(register_cerberus_ops: bool = True) -> types.ModuleType:
@@ -71,9 +76,9 @@ def _alias_cerberus_namespace():
     install._cerberus_lib = lib  # keep the registration alive
 
 
-def patch_flow_warp(modules: Iterable[str] = REFERENCE_MODEL_MODULES) -> int:
-    """Point the name ``flow_warp`` of every already-imported reference model module at the CUDA
-    kernel.  Returns how many modules were patched."""
+def patch_flow_warp(modules: Iterable[str] = REFERENCE_MODEL_MODULES + REFERENCE_LOSS_MODULES) -> int:
+    """Point the name ``flow_warp`` of every already-imported reference model AND loss module at the CUDA
+    kernel (differentiable with respect to image and flow).  Returns how many modules were patched."""
     n = 0
     for name in modules:
         mod = sys.modules.get(name)

@@ -16,6 +16,7 @@ from ._lib import (VARIANT_AUTO, WARP_TORCH, WARP_TORCH_CPU, WARP_TRT, CostVolum
                    device_guard, lib, make_params_cached as make_params, output_dims, ptr, require_cuda)
 
 __all__ = ["warp_corr_forward", "warp_corr_forward_upflow", "warp_corr_backward", "flow_warp_forward", "flow_warp_backward", "corr_output_shape",
+           "grid_sample_forward",
            "WARP_TORCH", "WARP_TRT", "WARP_TORCH_CPU"]
 
 
@@ -179,3 +180,32 @@ def flow_warp_backward(image: torch.Tensor, flow: torch.Tensor, grad_out: torch.
                                            ctypes.c_void_p(current_stream_ptr(image.device)))
     check(rc, "cerb_flow_warp_backward")
     return gimg, gflow
+
+
+_GRID_MODES = {"bilinear": 0, "nearest": 1}
+_GRID_PADS = {"zeros": 0, "border": 1, "reflection": 2}
+_GRID_CONVS = {"trt": 0, "aten": 1}
+
+
+def grid_sample_forward(input: torch.Tensor, grid: torch.Tensor, mode="bilinear", padding_mode="border",
+                        align_corners: bool = False, convention: str = "trt") -> torch.Tensor:
+    """Grid sampler with a normalised-coordinate grid (N,oH,oW,2), every mode of the reference's TensorRT plugin
+    (trt_plugins/grid_sampler.cu:146-271).  ``mode`` / ``padding_mode`` take PyTorch's strings or the plugin's
+    integers (grid_sampler.hpp:14-15).  ``convention='trt'`` un-normalises like the plugin
+    (``((g+1)*(size-1))/2`` for align_corners=False, ``roundf`` for nearest), ``'aten'`` like ``F.grid_sample``."""
+    require_cuda(input, grid)
+    if input.dim() != 4 or grid.dim() != 4 or grid.shape[0] != input.shape[0] or grid.shape[3] != 2:
+        raise CostVolumeError(f"expected input (N,C,H,W) and grid (N,oH,oW,2), got {tuple(input.shape)} / {tuple(grid.shape)}")
+    input = input.contiguous()
+    grid = grid.to(input.dtype).contiguous()
+    m = _GRID_MODES[mode] if isinstance(mode, str) else int(mode)
+    pm = _GRID_PADS[padding_mode] if isinstance(padding_mode, str) else int(padding_mode)
+    N, C, H, W = input.shape
+    oH, oW = grid.shape[1:3]
+    out = torch.empty(N, C, oH, oW, dtype=input.dtype, device=input.device)
+    with device_guard(input.device):
+        rc = lib().cerb_grid_sample_forward(ptr(input), ptr(grid), ptr(out), N, C, H, W, oH, oW, _lib.dtype_code(input), m, pm,
+                                            1 if align_corners else 0, _GRID_CONVS[convention],
+                                            ctypes.c_void_p(current_stream_ptr(input.device)))
+    check(rc, "cerb_grid_sample_forward")
+    return out

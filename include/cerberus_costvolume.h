@@ -155,6 +155,41 @@ CERB_API int cerb_flow_warp_backward(const void* image, const float* flow, const
                                      int32_t channels, int32_t height, int32_t width, int32_t dtype,
                                      int32_t warp_mode, cerb_stream_t stream);
 
+/* Stand-alone grid sampler with a GRID input (normalised coordinates), every mode of the reference's plugin.
+ * Replaces GridSamplerPlugin::enqueue / grid_sampler_kernel (runtime/cerberus_net/trt_plugins/grid_sampler.cu:146-271),
+ * the node the ONNX export emits for F.grid_sample (utilities/onnx_export.py:25-28).  The mode enumerations are the
+ * reference's (grid_sampler.hpp:14-15), i.e. PyTorch's.  `convention` picks the un-normalise / rounding rule:
+ * CERB_GRID_CONV_TRT = the plugin's own ((g+1)*(size-1))/2 for align_corners=0 and roundf for `nearest`
+ * (grid_sampler.cu:55-58,219-220); CERB_GRID_CONV_ATEN = what the same graph computes in PyTorch
+ * (((g+1)*size-1)/2, round-half-to-even).  input (N,C,H,W), grid (N,out_h,out_w,2) x then y, output
+ * (N,C,out_h,out_w), all contiguous and of `dtype`; coordinates are evaluated in fp32. */
+enum { CERB_GRID_BILINEAR = 0, CERB_GRID_NEAREST = 1 };
+enum { CERB_GRID_PAD_ZEROS = 0, CERB_GRID_PAD_BORDER = 1, CERB_GRID_PAD_REFLECTION = 2 };
+enum { CERB_GRID_CONV_TRT = 0, CERB_GRID_CONV_ATEN = 1 };
+CERB_API int cerb_grid_sample_forward(const void* input, const void* grid, void* output, int32_t batch,
+                                      int32_t channels, int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w,
+                                      int32_t dtype, int32_t interpolation_mode, int32_t padding_mode,
+                                      int32_t align_corners, int32_t convention, cerb_stream_t stream);
+
+/* Photometric term of unFlowLoss, fused: flow-warp + L1 + SSIM(3x3, reflection pad) + mean.
+ * Replaces, per scale and direction: flow_warp (UnFlowLoss.py:83-94,279-283), unFlowLoss.loss_photometric with the
+ * all-ones occlusion mask the reference runs with (UnFlowLoss.py:225-241,285-297), SSIM (loss_functions.py:47-78) and
+ * their autograd with respect to the flow.
+ *   loss = mean( l1_weight * |im_orig - rec| + ssim_weight * SSIM(rec, im_orig) ),  rec = flow_warp(im_src, flow)
+ * im_orig / im_src (N,C,H,W) fp32 contiguous, flow (N,2,H,W) fp32 contiguous, H, W >= 4.  `loss` is ONE float on the
+ * device; `workspace` holds cerb_photometric_workspace() bytes (per-tile partial sums, added in a fixed order: the
+ * result is bit-reproducible).  Backward: grad_flow (N,2,H,W) = d loss / d flow * grad_loss[0] (grad_loss: one float
+ * on the device); the images are inputs of the loss and get no gradient. */
+CERB_API size_t cerb_photometric_workspace(int32_t batch, int32_t height, int32_t width);
+CERB_API int cerb_photometric_forward(const float* im_orig, const float* im_src, const float* flow, float* loss,
+                                      void* workspace, size_t workspace_bytes, int32_t batch, int32_t channels,
+                                      int32_t height, int32_t width, float l1_weight, float ssim_weight,
+                                      int32_t warp_mode, cerb_stream_t stream);
+CERB_API int cerb_photometric_backward(const float* im_orig, const float* im_src, const float* flow,
+                                       const float* grad_loss, float* grad_flow, int32_t batch, int32_t channels,
+                                       int32_t height, int32_t width, float l1_weight, float ssim_weight,
+                                       int32_t warp_mode, cerb_stream_t stream);
+
 /* Same as cerb_warp_corr_forward but with HOST buffers (pinned or pageable): copies x1, x2
  * (and flow) host->device into `dev_workspace`, runs the fused kernel and copies the result
  * back, all asynchronously on `stream`.  This is the end-to-end call bench.py times.

@@ -89,6 +89,38 @@ CERB_API int cerb_trt_warp_corr_enqueue(const cerb_trt_corr_fields* f, int32_t w
                                         const cerb_trt_tensor_desc* output_desc, const void* const* inputs,
                                         void* const* outputs, void* workspace, cerb_stream_t stream);
 
+/* ---- fused warp_correlation node: plugin type "warp_correlation", version "1" (new; replaces the five nodes above).
+ * Fields: the six correlation ints, then warp_mode (kINT32, default CERB_WARP_TRT) and leaky_slope (kFLOAT32,
+ * default 0.1); serialised in that order, 32 bytes. */
+typedef struct cerb_trt_warp_corr_fields {
+  cerb_trt_corr_fields corr;
+  int32_t warp_mode;
+  float leaky_slope;
+} cerb_trt_warp_corr_fields;
+#define CERB_TRT_WARP_CORR_PLUGIN_TYPE "warp_correlation"
+#define CERB_TRT_WARP_CORR_PLUGIN_VERSION "1"
+CERB_API void cerb_trt_warp_corr_default_fields(cerb_trt_warp_corr_fields* f);
+CERB_API size_t cerb_trt_warp_corr_serialize(const cerb_trt_warp_corr_fields* f, void* buffer);   /* 32 bytes, NULL buffer = size query */
+CERB_API int cerb_trt_warp_corr_deserialize(const void* data, size_t length, cerb_trt_warp_corr_fields* f);
+
+/* ---- grid_sampler plugin: type "grid_sampler", version "1" (trt_plugins/grid_sampler.cpp:9-10).
+ * Fields align_corners, interpolation_mode, padding_mode, all kINT32 (grid_sampler.cpp:196-198); defaults false /
+ * Bilinear / Border (:40-42); serialisation = 1-byte bool + two ints = 9 bytes (:57-74).  The enumerations are
+ * CERB_GRID_* (grid_sampler.hpp:14-15). */
+typedef struct cerb_trt_grid_sampler_fields {
+  int32_t align_corners, interpolation_mode, padding_mode;
+} cerb_trt_grid_sampler_fields;
+#define CERB_TRT_GRID_SAMPLER_PLUGIN_TYPE "grid_sampler"
+#define CERB_TRT_GRID_SAMPLER_PLUGIN_VERSION "1"
+CERB_API void cerb_trt_grid_sampler_default_fields(cerb_trt_grid_sampler_fields* f);
+CERB_API size_t cerb_trt_grid_sampler_serialize(const cerb_trt_grid_sampler_fields* f, void* buffer);   /* 9 bytes, NULL buffer = size query */
+CERB_API int cerb_trt_grid_sampler_deserialize(const void* data, size_t length, cerb_trt_grid_sampler_fields* f);
+/* replaces GridSamplerPlugin::enqueue (grid_sampler.cu:238-271): inputs {input (N,C,H,W), grid (N,H,W,2)} of one
+ * type (kFLOAT or kHALF), output (N,C,H,W); the plugin's own un-normalise / rounding (CERB_GRID_CONV_TRT). */
+CERB_API int cerb_trt_grid_sampler_enqueue(const cerb_trt_grid_sampler_fields* f, const cerb_trt_tensor_desc* input_desc,
+                                           const cerb_trt_tensor_desc* output_desc, const void* const* inputs,
+                                           void* const* outputs, void* workspace, cerb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,8 +3,8 @@ Python surfaces, against the CPU oracle and the golden vectors on the same seede
 
 Tolerances (stated per SURVEY.md 8d / north_star: 1e-5 relative, fp32):
   fp32   max|diff| <= 1e-5 * max|ref|         (measured ~3e-7: summation order only)
-  fp16   max|diff| <= 2e-3 * max|ref|         (one half-precision rounding of the output)
-  bf16   max|diff| <= 1.6e-2 * max|ref|
+  fp16   max|diff| <= 6e-4 * max|ref|         (one rounding of the stored output: 2^-11 = 4.9e-4; fp32 accumulation)
+  bf16   max|diff| <= 5e-3 * max|ref|         (2^-8 = 3.9e-3)
 """
 import ctypes
 import math
@@ -180,7 +180,10 @@ def test_large_displacement_backward_vs_oracle(p, md, with_flow, dtype):
     # the oracle masks with its own forward; use ours so both see the same LeakyReLU sign pattern
     r1, r2, rf = co.level_backward(x1, x2, flow, g, p, 1, md, 1, 1, co.WARP_TORCH, 0.1)
     g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, tg, p, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1)
-    tol = TOL if dtype == torch.float32 else 3e-2
+    # bf16: max_displacement > 4 accumulates the nwin^2 (4 to 9) displacement windows in the STORED gradient, i.e. one
+    # bf16 rounding per window instead of one in total (2^-8 = 3.9e-3 of max each, adding in quadrature); the md = 4
+    # configuration every reference model uses rounds once (test_round2_parity.py::test_half_precision_backward_rounds_once)
+    tol = TOL if dtype == torch.float32 else 1e-2
     assert rel_err(g1.float().cpu().numpy(), r1) < tol
     assert rel_err(g2.float().cpu().numpy(), r2) < tol
     if with_flow:
@@ -330,7 +333,7 @@ def test_flow_far_outside_every_border():
 
 
 # ------------------------------------------------------------------ dtypes, strides, surfaces
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 6e-4), (torch.bfloat16, 5e-3)])
 @pytest.mark.parametrize("with_flow", [False, True])
 def test_half_precision_io(dtype, tol, with_flow):
     """16-bit inputs/outputs, fp32 accumulation (the reference accumulates fp16 in fp16,
@@ -346,7 +349,7 @@ def test_half_precision_io(dtype, tol, with_flow):
         assert rel_err(out.float().cpu().numpy(), ref) < tol
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 6e-4), (torch.bfloat16, 5e-3)])
 @pytest.mark.parametrize("shape", [(1, 32, 40, 72), (2, 12, 19, 37), (1, 8, 64, 128), (1, 16, 24, 44)])
 @pytest.mark.parametrize("flow_kind", ["none", "iid", "big"])
 def test_half_precision_tma_paths(dtype, tol, shape, flow_kind):
@@ -474,7 +477,7 @@ def test_trt_enqueue_adapter_and_host_call():
     outs = (ctypes.c_void_p * 1)(outh.data_ptr())
     assert lib.cerb_trt_corr_enqueue(ctypes.byref(f), descs, ctypes.byref(descs[3]), ins, outs, None, stream) == 0
     torch.cuda.synchronize()
-    assert rel_err(outh.float().cpu().numpy(), co.corr_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), 4, 1, 4, 1, 1)) < 2e-3
+    assert rel_err(outh.float().cpu().numpy(), co.corr_forward(h1.float().cpu().numpy(), h2.float().cpu().numpy(), 4, 1, 4, 1, 1)) < 6e-4
     # fused warp_correlation node, TensorRT warp convention
     for i in (0, 1, 3):
         descs[i].type = 0
@@ -567,7 +570,7 @@ def test_full_size_fused_against_stock_composition():
         assert rel_err(cb.flow_warp(x2, fl).cpu().numpy(), warped.cpu().numpy()) < 2e-6
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.bfloat16, 5e-3)])
 @pytest.mark.parametrize("md", [4, 8])
 def test_many_tiles_per_cta_persistent_loop(dtype, tol, md):
     """More work units than CTAs (768 tiles of 8x32, x4 displacement windows for md = 8): every CTA walks
