@@ -22,7 +22,7 @@ from typing import Iterable
 import torch
 
 from . import correlation as _correlation
-from . import flow_warp as _flow_warp
+from .flow_warp import flow_warp as _flow_warp_fn   # (the package re-exports the function under the sub-module's name)
 
 REFERENCE_CORRELATION_MODULE = "nnet_training.correlation_package.correlation"
 REFERENCE_MODEL_MODULES = (
@@ -83,6 +83,6 @@ def patch_flow_warp(modules: Iterable[str] = REFERENCE_MODEL_MODULES + REFERENCE
     for name in modules:
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "flow_warp"):
-            mod.flow_warp = _flow_warp.flow_warp
+            mod.flow_warp = _flow_warp_fn
             n += 1
     return n
