@@ -317,6 +317,104 @@ def run_train_block(dev, rank, world, local_rank, steps=8, warmup=3, batch=8):
             "last_loss": last}
 
 
+# ------------------------------------------------------------------------------ BASELINE configs[2] and [4]
+def run_other_configs(dev, lib, fma_peak, hbm_peak):
+    """The other BASELINE configurations, in the driver-run record (rank 0, N=1):
+    configs[2] -- the part that runs without TensorRT: the plugin-`enqueue`-shaped entries on the HRNetV2-W48 level
+                  shapes at 1024x512, batch 1, kFLOAT and kHALF, CUDA-graph replays (no syncs, no private streams);
+    configs[4] -- KITTI-shaped 1248x384 (HRNet pyramid, incl. the unaligned W = 78 level) and 1280x384 (PWC) finest
+                  levels at max_displacement 8 (289 planes), batch 32, forward and backward."""
+    import cerberusnet_b200 as cb
+    from cerberusnet_b200 import _lib, ops
+    F = torch.nn.functional
+    f = _lib.TrtCorrFields()
+    lib.cerb_trt_corr_default_fields(ctypes.byref(f))
+
+    def graph_time(fn, reps=100):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            sp = ctypes.c_void_p(st.cuda_stream)
+            fn(sp)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=st):
+                for _ in range(10):
+                    fn(sp)
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps // 10):
+                g.replay()
+            e1.record(st)
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    trt = {"levels": [], "note": "plugin enqueue entries (cerb_trt_corr_enqueue / cerb_trt_warp_corr_enqueue, TensorRT "
+                                 "un-normalise), HRNetV2-W48 level shapes, batch 1, CUDA-graph replays; TensorRT itself is "
+                                 "not in the image, so this is the plugin half of configs[2] only"}
+    tot = {"kFLOAT": 0.0, "kHALF": 0.0}
+    for (C, H, W, wp) in ((384, 16, 32, False), (192, 32, 64, True), (96, 64, 128, True), (48, 128, 256, True)):
+        row = {"C": C, "H": H, "W": W}
+        for name, dt, code in (("kFLOAT", torch.float32, 0), ("kHALF", torch.float16, 1)):
+            x1 = F.leaky_relu(torch.randn(1, C, H, W, device=dev), 0.1).to(dt)
+            x2 = F.leaky_relu(torch.randn(1, C, H, W, device=dev), 0.1).to(dt)
+            fl = (torch.randn(1, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+            out = torch.empty(1, 81, H, W, device=dev, dtype=dt)
+            descs = (_lib.TrtTensorDesc * 4)()
+            for i, dims in enumerate(((1, C, H, W), (1, C, H, W), (1, 2, H, W), (1, 81, H, W))):
+                descs[i].dims.nbDims = 4
+                for j, v in enumerate(dims):
+                    descs[i].dims.d[j] = v
+                descs[i].type = code if i != 2 else 0
+            ins = (ctypes.c_void_p * 3)(x1.data_ptr(), x2.data_ptr(), fl.data_ptr())
+            outs = (ctypes.c_void_p * 1)(out.data_ptr())
+
+            def plain(sp):
+                assert lib.cerb_trt_corr_enqueue(ctypes.byref(f), descs, ctypes.byref(descs[3]), ins, outs, None, sp) == 0
+
+            def fused(sp):
+                assert lib.cerb_trt_warp_corr_enqueue(ctypes.byref(f), 1, 0.1, descs, ctypes.byref(descs[3]), ins, outs, None, sp) == 0
+
+            row[name + "_corr_node_us"] = round(graph_time(plain), 2)
+            if wp:
+                row[name + "_fused_node_us"] = round(graph_time(fused), 2)
+            tot[name] += row[name + ("_fused_node_us" if wp else "_corr_node_us")]
+        trt["levels"].append(row)
+    trt["pyramid_us"] = {k: round(v, 1) for k, v in tot.items()}
+
+    def timeit(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / reps
+
+    kitti = []
+    for (C, H, W, B) in ((32, 96, 320, 32), (48, 96, 312, 32), (192, 24, 78, 32)):
+        x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
+        x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
+        fl = (torch.randn(B, 2, H, W, device=dev) * 1.5).clamp_(-6, 6)
+        out = torch.empty(B, 289, H, W, device=dev)
+        tf = timeit(lambda: ops.warp_corr_forward(x1, x2, fl, 8, 1, 8, 1, 1, 1, cb.WARP_TORCH, SLOPE, out=out), 5)
+        gg = torch.randn_like(out)
+        tb = timeit(lambda: ops.warp_corr_backward(x1, x2, fl, out, gg, 8, 1, 8, 1, 1, 1, cb.WARP_TORCH, SLOPE), 3)
+        flops, byts = 2 * B * H * W * C * 289, B * H * W * 4 * (2 * C + 289 + 2)
+        bbytes = B * H * W * 4 * (2 * 289 + 4 * C + 4)
+        kitti.append({"C": C, "H": H, "W": W, "batch": B, "max_displacement": 8, "fwd_us": round(tf, 1),
+                      "fwd_TFLOPs": round(flops / tf / 1e6, 2), "fwd_fma_frac": round(flops / tf / 1e6 / fma_peak, 4),
+                      "fwd_hbm_frac": round(byts / tf / 1e3 / hbm_peak, 4), "bwd_us": round(tb, 1),
+                      "bwd_TFLOPs": round(2 * flops / tb / 1e6, 2), "bwd_hbm_frac": round(bbytes / tb / 1e3 / hbm_peak, 4),
+                      "tma_rows_aligned": W % 4 == 0})
+        del x1, x2, fl, out, gg
+    torch.cuda.empty_cache()
+    return {"configs2_trt_plugin_entries": trt, "configs4_kitti_md8": kitti}
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main_gpu(args, rank, world, local_rank):
     from cerberusnet_b200.parallel import bind_to_gpu_numa
@@ -590,6 +688,10 @@ def main_gpu(args, rank, world, local_rank):
                         "sample": sample + ", pure-PyTorch restatement (oracle/torch_oracle.py), fp32",
                         "ms_per_step": ms}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_other_configs:
+        other = run_other_configs(dev, lib, fma_peak, hbm_peak)
+
     # ---- the multi-GPU split north_star names: DDP training step
     train = None
     if not args.no_train:
@@ -606,6 +708,7 @@ def main_gpu(args, rank, world, local_rank):
             "launches_per_step": int(launches_per_step),
             "roofline": roofline, "roofline_bwd": roofline_bwd, "levels": level_stats, "levels_smooth": level_stats_smooth,
             "levels_one_direction": level_stats_one, "cpu_baseline": cpu_baseline, "e2e": e2e, "train": train,
+            "other_configs": other,
             "gpu_launches": int(launches_per_step) * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -623,6 +726,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

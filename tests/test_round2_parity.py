@@ -83,6 +83,7 @@ def test_hrnet_training_shapes_batch8_fused_vs_oracle(shape):
     t1, t2, tf = (torch.from_numpy(a).to(dev()) for a in (x1, x2, fl))
     out = ops.warp_corr_forward(t1, t2, tf, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
     g = rs.standard_normal(out.shape).astype(np.float32)
+    g[np.abs(out.cpu().numpy()) < 1e-6 * float(out.abs().max())] = 0.0   # outputs within rounding of zero: LeakyReLU sign is not defined
     g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, torch.from_numpy(g).to(dev()), 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
     for n in (0, B - 1):
         s = slice(n, n + 1)
@@ -111,6 +112,9 @@ def test_kitti_md8_shapes_incl_unaligned_widths(shape, with_flow):
     ref = co.level_forward(x1, x2, fl, 8, 1, 8, 1, 1, co.WARP_TORCH, 0.1)
     assert rel_err(out.cpu().numpy(), ref) < TOL
     g = rs.standard_normal(ref.shape).astype(np.float32)
+    # the oracle masks the LeakyReLU with its OWN forward: where that is within rounding of zero (one output in ~17 M
+    # here) the two sign patterns may differ legitimately, so no gradient is sent through those outputs
+    g[np.abs(ref) < 1e-6 * np.abs(ref).max()] = 0.0
     g1, g2, gf = ops.warp_corr_backward(t1, t2, tf, out, torch.from_numpy(g).to(dev()), 8, 1, 8, 1, 1, 1, cb.WARP_TORCH, 0.1)
     r1, r2, rf = co.level_backward(x1, x2, fl, g, 8, 1, 8, 1, 1, co.WARP_TORCH, 0.1)
     assert rel_err(g1.cpu().numpy(), r1) < TOL and rel_err(g2.cpu().numpy(), r2) < TOL
