@@ -16,7 +16,7 @@ from . import build as _build
 
 CERB_F32, CERB_F16, CERB_BF16 = 0, 1, 2
 WARP_TORCH, WARP_TRT, WARP_TORCH_CPU = 0, 1, 2
-VARIANT_AUTO, VARIANT_FAST, VARIANT_FAST_NOTMA, VARIANT_SMALL, VARIANT_SMALL_NOTMA, VARIANT_GENERIC = range(6)
+VARIANT_AUTO, VARIANT_FAST, VARIANT_FAST_NOTMA, VARIANT_SMALL, VARIANT_SMALL_NOTMA, VARIANT_GENERIC, VARIANT_MID, VARIANT_TC = range(8)
 
 _DTYPES = {torch.float32: CERB_F32, torch.float16: CERB_F16, torch.bfloat16: CERB_BF16}
 

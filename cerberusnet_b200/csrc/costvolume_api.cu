@@ -150,7 +150,7 @@ CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const voi
   const int rc = build_geom(p, flow != nullptr, g);
   if (rc != CERB_OK) return rc;
   if (!x1 || !x2 || !out) return CERB_EINVAL;
-  if (variant < CERB_FWD_VARIANT_AUTO || variant > CERB_FWD_VARIANT_MID) return CERB_EINVAL;
+  if (variant < CERB_FWD_VARIANT_AUTO || variant > CERB_FWD_VARIANT_TC) return CERB_EINVAL;
   if (variant != CERB_FWD_VARIANT_AUTO && variant != CERB_FWD_VARIANT_GENERIC && !is_fast(g)) return CERB_EUNSUPPORTED;
   const cudaError_t e = launch_warp_corr_forward(g, p->dtype, x1, x2, flow, out, variant, (cudaStream_t)stream);
   if (e == cudaSuccess) count_launches(1);

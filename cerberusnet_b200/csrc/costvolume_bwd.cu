@@ -50,6 +50,12 @@ struct BwdArgs {
   int async_ok[2];         // fp32 and 16-byte alignment of s[] rows: stage the halo tiles with cp.async
   int vec4_ok[2];          // 16-bit and 8-byte alignment of s[] rows: stage the halo tiles with 4-element loads
   int s_roll[2], g_roll[2]; // batch-item roll applied when reading s[] / writing gdst[] (x2_batch_roll when they are x2 / grad_x2 themselves)
+  // fused warp backward (phase 1 of the fused kernel): the gradient with respect to the warped map stays on chip and is
+  // splatted through the bilinear taps straight into grad_x2, the flow gradient is reduced over the channels
+  const void* x2;          // the un-warped second map (tap values for the flow gradient)
+  const float* flow;
+  void* gx2;               // splat target: grad_x2 (fp32 input) or the fp32 accumulator (16-bit inputs), zeroed by the launcher
+  float* gflow;
 };
 
 // Register-tiled backward of the correlation.  Both gradients have the form
@@ -83,12 +89,14 @@ struct BwdCfg {
   static_assert(BCH * BS_CH >= BG_FLOATS, "the saved-output tile borrows the S buffer");
 };
 
-template <typename T, int WHICH, int TYB>
-__global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_kernel(const BwdArgs a) {
+// SPLAT (WHICH == 1 only): instead of writing the gradient with respect to the (warped) second input, every thread
+// pushes its pixel's values through the four bilinear taps into grad_x2 (red.global.add) and accumulates the flow
+// gradient over the channels -- the stand-alone warp-backward kernel and its workspace round trip folded in.
+template <typename T, typename GT, int WHICH, int TYB, bool SPLAT>
+__device__ __forceinline__ void corr_bwd_phase(const BwdArgs& a, float* bsm) {
   using Cfg = BwdCfg<TYB>;
   constexpr int BT_Y = Cfg::BT_Y, BH_Y = Cfg::BH_Y, NT = Cfg::NT, BS_CH = Cfg::BS_CH, BO_CH = Cfg::BO_CH,
                 BG_FLOATS = Cfg::BG_FLOATS;
-  extern __shared__ __align__(16) float bsm[];
   float* Gs = bsm;                  // [81][8][32]
   float* Ss = bsm + BG_FLOATS;      // [32][BS_CH]   (aliased by the staged output [32][BO_CH])
   const Geom& g = a.g;
@@ -102,6 +110,23 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
   const T* __restrict__ outp = a.out ? (const T*)a.out + (long long)n * g.os[0] : nullptr;
   const bool mask = g.has_act && outp != nullptr;
   constexpr bool kF32 = std::is_same<T, float>::value;
+
+  // ---- SPLAT: sampling data of this thread's pixel (thread = pixel of the tile), fixed for all channels and windows
+  Taps tp_in, tp_out;             // taps into x2 (its strides) / into the contiguous gradient
+  float s_wx1 = 0.f, s_wx0 = 0.f, s_wy1 = 0.f, s_wy0 = 0.f, gix = 0.f, giy = 0.f;
+  bool s_bx1 = false, s_by1 = false, s_inx = false, s_iny = false;
+  const int n_x2 = (n + g.x2roll) % g.B;   // batch item of x2 / grad_x2 paired with item n
+  if constexpr (SPLAT) {
+    const int sy_ = min(iy0 + (tid >> 5), g.H - 1), sx_ = min(ix0 + (tid & 31), g.W - 1);
+    const float* fp = a.flow + (long long)n * g.fls[0] + (long long)sy_ * g.fls[2] + sx_;
+    const float sx = sample_pos(sx_, __ldg(fp), g.W, g.warp_mode, s_inx);
+    const float sy = sample_pos(sy_, __ldg(fp + g.fls[1]), g.H, g.warp_mode, s_iny);
+    tp_in = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
+    tp_out = make_taps(sx, sy, g.H, g.W, g.W);
+    const float fx = floorf(sx), fy = floorf(sy);
+    s_wx1 = fx + 1.f - sx; s_wx0 = sx - fx; s_wy1 = fy + 1.f - sy; s_wy0 = sy - fy;
+    s_bx1 = (int)fx + 1 < g.W; s_by1 = (int)fy + 1 < g.H;
+  }
 
   // max_displacement > 4: the D x D displacement range is covered by 9 x 9 windows (origins 0, 8, ...,
   // D - 9, as in the forward); the windows' contributions are accumulated into the output, rows /
@@ -352,6 +377,41 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
     __syncthreads();
 
     if (c0 == 0) BWD_TRACE(WHICH * 32 + 4);
+    if constexpr (SPLAT) {
+      // ---- splat: the chunk's gradient with respect to the warped map goes through the taps of this thread's pixel
+      if (wpix_ok) {
+        const float* orow = Os + wty * BT_X + wtx;
+        const T* x2n = (const T*)a.x2 + (long long)n_x2 * g.x2s[0];
+        GT* gx2n = (GT*)a.gx2 + (long long)n_x2 * g.C * plane_elems;
+        for (int c4 = 0; c4 < cmax; c4 += 4) {   // 4 channels per batch: 16 independent tap loads in flight
+          float gvv[4], v[4][4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = min(c4 + k, cmax - 1);
+            gvv[k] = orow[c * BO_CH];
+            const T* pch = x2n + (long long)(c0 + c) * g.x2s[1];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) v[k][q] = ldg_f32(pch + tp_in.off[q]);   // clamped taps: always valid addresses
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (c4 + k < cmax) {
+              GT* gp = gx2n + (long long)(c0 + c4 + k) * plane_elems;
+              if (tp_out.w[0] != 0.f) atomic_add_t<GT>(gp + tp_out.off[0], gvv[k] * tp_out.w[0]);
+              if (tp_out.w[1] != 0.f) atomic_add_t<GT>(gp + tp_out.off[1], gvv[k] * tp_out.w[1]);
+              if (tp_out.w[2] != 0.f) atomic_add_t<GT>(gp + tp_out.off[2], gvv[k] * tp_out.w[2]);
+              if (tp_out.w[3] != 0.f) atomic_add_t<GT>(gp + tp_out.off[3], gvv[k] * tp_out.w[3]);
+              const float v_nw = v[k][0];
+              const float v_ne = s_bx1 ? v[k][1] : 0.f;
+              const float v_sw = s_by1 ? v[k][2] : 0.f;
+              const float v_se = (s_bx1 && s_by1) ? v[k][3] : 0.f;
+              gix += gvv[k] * ((v_ne - v_nw) * s_wy1 + (v_se - v_sw) * s_wy0);
+              giy += gvv[k] * ((v_sw - v_nw) * s_wx1 + (v_se - v_ne) * s_wx0);
+            }
+          }
+        }
+      }
+    } else
     // ---- write-out: one pixel per thread, channels of the chunk (rows of 32 pixels: coalesced)
     if (wpix_ok) {
       const float* orow = Os + wty * BT_X + wtx;
@@ -367,7 +427,33 @@ __global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_ker
     }
   }
   }  // displacement windows
+  if constexpr (SPLAT) {
+    const int sy_ = iy0 + (tid >> 5), sx_ = ix0 + (tid & 31);
+    if (sy_ < g.H && sx_ < g.W) {
+      float* gf = a.gflow + (long long)n * 2 * g.H * g.W + (long long)sy_ * g.W + sx_;
+      gf[0] = s_inx ? gix * pos_scale(g.W, g.warp_mode) : 0.f;
+      gf[(long long)g.H * g.W] = s_iny ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
+    }
+  }
   BWD_TRACE(WHICH * 32 + 5);
+}
+
+// one gradient per launch (kept for the two-launch path: no flow, or debugging)
+template <typename T, int WHICH, int TYB>
+__global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_tiled_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) float bsm[];
+  corr_bwd_phase<T, T, WHICH, TYB, false>(a, bsm);
+}
+
+// Both gradients of a tile in one CTA: grad_x1 first, then -- the 81 planes of grad_out / out it needs are the ones just
+// read, shifted by at most 4 pixels, so they come from L2 -- the gradient with respect to the second input, which with a
+// flow never leaves the chip: it is splatted into grad_x2 and reduced into grad_flow right here.
+template <typename T, typename GT, int TYB, bool SPLAT>
+__global__ void __launch_bounds__(32 * TYB, TYB == 4 ? 2 : 1) corr_bwd_fused_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) float bsm[];
+  corr_bwd_phase<T, T, 0, TYB, false>(a, bsm);
+  __syncthreads();
+  corr_bwd_phase<T, GT, 1, TYB, SPLAT>(a, bsm);
 }
 
 // ------------------------------------------------------------------ generic backward ------

@@ -47,6 +47,7 @@ long long* get_trace_buffer() { return g_trace_buffer; }
 static int g_trace_iter = 0;
 static unsigned long long* g_path_counters = nullptr;  // optional: tiles per staging path (bench.py reports the fallback rate)
 void set_path_counters(unsigned long long* p) { g_path_counters = p; }
+unsigned long long* get_path_counters() { return g_path_counters; }
 void set_trace_iter(int it) { g_trace_iter = it; }
 // records only the `dbg_iter`-th tile processed by each CTA (every role keeps its own `titer`)
 constexpr int kTraceSlots = 192;  // clock64 slots per CTA in the debugging trace
@@ -1314,8 +1315,15 @@ static PFN_encodeTiled get_encode_fn() {
 
 // fp32 NCHW (W-stride 1) tensor map with box {bx, by, bc, 1}
 // 4-D (x, y, c, n) tiled tensor map over an NCHW tensor of `esize`-byte elements
+bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
+                    const long long strides[3], int bx, int by, int bc, bool swizzle128);
 static bool make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
                       const long long strides[3], int bx, int by, int bc, bool swizzle128) {
+  return make_tmap_nchw(tm, dt, esize, base, W, H, C, B, strides, bx, by, bc, swizzle128);
+}
+// (also used by costvolume_fwd_tc.cu)
+bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
+                    const long long strides[3], int bx, int by, int bc, bool swizzle128) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return false;
   if (((uintptr_t)base & 15) != 0) return false;
@@ -1365,6 +1373,8 @@ static int num_sms() {
   if (dev >= 0 && dev < 64) cache[dev] = v;
   return v;
 }
+
+int num_sms_current() { return num_sms(); }   // costvolume_fwd_tc.cu
 
 template <typename T, int TY, int TX, int KS, int CC, int RS, bool UP>
 static const void* kern_for_query() { return (const void*)warp_corr_fwd_kernel<T, TY, TX, KS, CC, RS, UP>; }
@@ -1525,6 +1535,20 @@ template <typename T>
 static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
                                 int variant, cudaStream_t stream, const UpFlow* uf) {
   const bool fast_ok = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= kMD && variant != CERB_FWD_VARIANT_GENERIC;
+  // tensor-core variant (costvolume_fwd_tc.cu): on request, or when there are enough 8 x 16 tiles to keep every SM's
+  // staging / MMA / drain pipeline full
+  {
+    const int dt = std::is_same<T, float>::value ? CERB_F32 : (std::is_same<T, __half>::value ? CERB_F16 : CERB_BF16);
+    if (variant == CERB_FWD_VARIANT_TC) {
+      if (!tc_forward_supported(g, dt, uf)) return cudaErrorNotSupported;
+      return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream);
+    }
+    static const int tc_env = getenv("CERB_FWD_TC") ? atoi(getenv("CERB_FWD_TC")) : -1;   // 0: never, 1: whenever supported
+    if (variant == CERB_FWD_VARIANT_AUTO && tc_env != 0 && tc_forward_supported(g, dt, uf) && flow != nullptr) {
+      const long long tiles = (long long)g.B * ((g.outW + 15) / 16) * ((g.outH + 7) / 8);
+      if (tc_env == 1 || tiles >= 256) return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream);
+    }
+  }
   if (fast_ok) {
     const int no_tma = (variant == CERB_FWD_VARIANT_FAST_NOTMA || variant == CERB_FWD_VARIANT_SMALL_NOTMA) ? 1 : 0;
     bool small = variant == CERB_FWD_VARIANT_SMALL || variant == CERB_FWD_VARIANT_SMALL_NOTMA;

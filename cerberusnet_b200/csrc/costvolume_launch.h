@@ -14,7 +14,8 @@ enum {
   CERB_FWD_VARIANT_SMALL = 3,       // 4x16 tiles, channels split 4-way inside the CTA
   CERB_FWD_VARIANT_SMALL_NOTMA = 4,
   CERB_FWD_VARIANT_GENERIC = 5,     // one thread per output element, any parameters
-  CERB_FWD_VARIANT_MID = 6          // 8x16 tiles, channels split 2-way inside the CTA
+  CERB_FWD_VARIANT_MID = 6,         // 8x16 tiles, channels split 2-way inside the CTA
+  CERB_FWD_VARIANT_TC = 7           // tensor cores (tcgen05 / TMEM): 8x16 tiles as 128 x 384 Gram tiles, 3xTF32 for fp32
 };
 
 namespace cerb {
@@ -31,6 +32,11 @@ struct UpFlow {
 
 cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
                                      void* out, int variant, cudaStream_t stream, const UpFlow* upflow = nullptr);
+
+// tensor-core forward (costvolume_fwd_tc.cu)
+bool tc_forward_supported(const Geom& g, int dtype, const UpFlow* upflow);
+cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
+                                        cudaStream_t stream);
 
 // workspace: fp32 [B,C,H,W] accumulation buffer for grad_x2 when dtype is 16-bit and flow != NULL
 cudaError_t launch_warp_corr_backward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,
