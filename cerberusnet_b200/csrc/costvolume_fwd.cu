@@ -1535,18 +1535,19 @@ template <typename T>
 static cudaError_t launch_fwd_t(const Geom& g, const void* x1, const void* x2, const float* flow, void* out,
                                 int variant, cudaStream_t stream, const UpFlow* uf) {
   const bool fast_ok = g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md >= kMD && variant != CERB_FWD_VARIANT_GENERIC;
-  // tensor-core variant (costvolume_fwd_tc.cu): on request, or when there are enough 8 x 16 tiles to keep every SM's
-  // staging / MMA / drain pipeline full
+  // tensor-core variant (costvolume_fwd_tc.cu): on request, or when there are at least 64 tiles of 8 x 16 (measured on
+  // B200, both flow directions per launch: 64 tiles 15.1 vs 15.6 us, 128 tiles 15.4 vs 23.6, 512 tiles 29.9 vs 32.6;
+  // 32 tiles 18.9 vs 14.1 -- the cluster-split CUDA-core kernel keeps the coarse levels)
   {
     const int dt = std::is_same<T, float>::value ? CERB_F32 : (std::is_same<T, __half>::value ? CERB_F16 : CERB_BF16);
     if (variant == CERB_FWD_VARIANT_TC) {
       if (!tc_forward_supported(g, dt, uf)) return cudaErrorNotSupported;
-      return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream);
+      return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream, uf);
     }
     static const int tc_env = getenv("CERB_FWD_TC") ? atoi(getenv("CERB_FWD_TC")) : -1;   // 0: never, 1: whenever supported
-    if (variant == CERB_FWD_VARIANT_AUTO && tc_env != 0 && tc_forward_supported(g, dt, uf) && flow != nullptr) {
+    if (variant == CERB_FWD_VARIANT_AUTO && tc_env != 0 && tc_forward_supported(g, dt, uf) && (flow != nullptr || uf != nullptr)) {
       const long long tiles = (long long)g.B * ((g.outW + 15) / 16) * ((g.outH + 7) / 8);
-      if (tc_env == 1 || tiles >= 256) return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream);
+      if (tc_env == 1 || tiles >= 64) return launch_warp_corr_forward_tc(g, dt, x1, x2, flow, out, stream, uf);
     }
   }
   if (fast_ok) {

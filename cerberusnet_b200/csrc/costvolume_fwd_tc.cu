@@ -13,20 +13,25 @@
 //   fp32 inputs:  "3xTF32" -- every operand is split hi = tf32(v), lo = v - hi and three products (hi*hi, lo*hi,
 //                 hi*lo) accumulate in fp32: measured 4e-7 of max|ref| (tools/microbench/umma_probe.cu), inside the
 //                 1e-5 parity bar.  A single TF32 product (3e-4) is not.
-// Roles (18 warps, one CTA per SM, persistent over tiles):
-//   warps 0-3   thread = pixel.  Stage the x1 tile K-major (hi / lo) per K step of 8 channels; after the tile's last MMA
-//               drain TMEM: warp w owns TMEM lanes 32w..32w+31 (pixel rows 2w, 2w+1), loads the 10 halo rows it needs
-//               24 columns at a time (tcgen05.ld 32x32b), shifts the row by its own x with a 4-stage select network
-//               (the column offset differs per lane, tcgen05.ld's does not), divides, activates, stores.
-//   warps 4-15  thread = halo position.  Flow -> sample position -> 4 taps + weights once per tile; per K step the taps
-//               of 8 channels from the raw x2 box in shared memory (or straight from global memory when the tile's
-//               footprint does not fit the box), blend in ATen's order, split, four 16-byte stores into the K-major
-//               128B-swizzled operand rows.  The warped map never exists in HBM.
-//   warp 16     one lane issues tcgen05.mma.kind::tf32 (M 128, N 192 x 2, K 8): 6 per K step; tcgen05.commit releases
+// Roles (22 warps, one CTA per SM, persistent over tiles):
+//   warps 0-7   accumulator drain, thread = pixel: warps w and w + 4 own TMEM lanes 32(w%4).. (pixel rows 2(w%4), +1) and
+//               six / four of the ten halo rows those need; 24 columns at a time (tcgen05.ld 32x32b), the row is shifted
+//               by the lane's own x with a 4-stage select network (the column offset differs per lane, tcgen05.ld's does
+//               not), then divide, activate, store.  Warps 4-7 also stage the x1 operand: LDG in one burst per 32
+//               channels, hi / lo split, tcgen05.st into TMEM columns 384.. (the A operand is read from tensor memory:
+//               it never touches shared memory, whose bandwidth is what bounds this kernel).
+//   warps 8-19  thread = halo position.  Flow -> sample position -> 4 taps + weights once per tile (the next tile's are
+//               prepared during this tile's first K step); per K step of 8 channels the taps from the raw x2 box in
+//               shared memory (or straight from global memory when the tile's footprint does not fit the box), blend in
+//               ATen's order, hi / lo split, four 16-byte stores into the K-major 128B-swizzled operand rows.  The warped
+//               map never exists in HBM.
+//   warp 20     one lane issues tcgen05.mma.kind::tf32 (M 128, N 192 x 2, K 8): 6 per K step; tcgen05.commit releases
 //               the operand slot / publishes the accumulator.
-//   warp 17     one lane issues the raw-box TMA loads (box origin from the tile's tap bounding box).
+//   warp 21     one lane issues the TMA load of a K step's raw x2 box (8 ch x 30 x 44, origin from the tile's tap
+//               bounding box), three in flight.
 // Operand slots: a 128-byte operand row holds 32 channels = 4 K steps; slot j of every row is refilled as soon as the
-// MMAs that read it have retired, so staging, MMA and the previous tile's drain overlap.
+// MMAs that read it have retired, so staging, MMA and the previous tile's drain overlap.  The accumulator itself is
+// single-buffered (384 of TMEM's 512 columns, 64 more hold the x1 operand): MMAs of tile t+1 start when tile t has drained.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -51,21 +56,25 @@ constexpr int TY = 8, TX = 16, M = TY * TX;           // output tile, MMA M
 constexpr int MD = 4;
 constexpr int HY = TY + 2 * MD, HX = TX + 2 * MD;     // 16 x 24 halo of the second map
 constexpr int N = HY * HX, NH = N / 2;                // 384 accumulator columns, two MMAs of N = 192
-constexpr int MARGIN = 6;                             // flow variation (px) inside one halo the raw box absorbs
+#ifndef CERB_TC_MARGIN
+#define CERB_TC_MARGIN 6
+#endif
+constexpr int MARGIN = CERB_TC_MARGIN;                // flow variation (px) inside one halo the raw box absorbs
 constexpr int RAW_H = HY + 2 * MARGIN + 2;            // 30
 constexpr int RAW_W = (HX + 2 * MARGIN + 2 + 3 + 3) / 4 * 4;   // 44 (box starts are 16-byte aligned)
 constexpr int KC = 8;                                 // channels per K step (32 bytes of a K-major row = one tf32 MMA)
 constexpr int SLOTS = 4;                              // K steps per 128-byte operand row
-constexpr int RS = 2;                                 // raw boxes in flight
-constexpr int EPI_WARPS = 4, GATHER_WARPS = 12;
+constexpr int RS = 3;                                 // raw boxes in flight
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 12, A_WARPS = 4;   // drain / gather / (of the gather warps) x1 conversion
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, TMA_WARP = MMA_WARP + 1;
-constexpr int NTHREADS = (TMA_WARP + 1) * 32;         // 576
-constexpr uint32_t A_BYTES = M * 128, B_BYTES = N * 128;
-constexpr uint32_t OFF_AHI = 0, OFF_ALO = A_BYTES, OFF_BHI = 2 * A_BYTES, OFF_BLO = 2 * A_BYTES + B_BYTES;
-constexpr uint32_t OFF_RAW = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int NTHREADS = (TMA_WARP + 1) * 32;         // 704
+constexpr uint32_t B_BYTES = N * 128;
+constexpr uint32_t OFF_BHI = 0, OFF_BLO = B_BYTES;
+constexpr uint32_t OFF_RAW = 2 * B_BYTES;
+constexpr uint32_t TMEM_A = N;                        // x1 operand: TMEM columns 384 + 16 slot (8 hi, 8 lo)
 constexpr uint32_t RAW_PLANE = RAW_H * RAW_W * 4;
-constexpr uint32_t RAW_STAGE = KC * RAW_PLANE;
+constexpr uint32_t RAW_STAGE = KC * RAW_PLANE;        // raw x2 box of a K step
 constexpr uint32_t OFF_RED = OFF_RAW + RS * RAW_STAGE;
 constexpr uint32_t OFF_BAR = OFF_RED + 2 * GATHER_WARPS * 4 * 4;
 constexpr int NBARS = 3 * SLOTS + 2 * RS + 2 + 4;
@@ -73,7 +82,7 @@ constexpr uint32_t OFF_TMEM = OFF_BAR + NBARS * 8;
 constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
 static_assert(RAW_STAGE % 128 == 0 && OFF_RAW % 1024 == 0, "TMA destination alignment");
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(N == GATHER_THREADS && M == EPI_WARPS * 32, "one halo position / one pixel per thread");
+static_assert(N == GATHER_THREADS && M == A_WARPS * 32 && EPI_WARPS == 8, "one halo position / one pixel per thread");
 
 enum { PATH_RAW = 1, PATH_DIRECT = 2 };   // indices match costvolume_fwd.cu's path counters
 
@@ -87,6 +96,13 @@ struct Args {
   int tiles_x, tiles_y, total_tiles;
   int nks;              // K steps per tile: ceil(C / 8)
   int use_raw;          // raw x2 boxes by TMA
+  // fused flow up-sampling (cerb_warp_corr_forward_upflow): coarse flow in, up-sampled flow out (cflow == nullptr: off)
+  const float* cflow;
+  long long cfs[3];
+  int Hc, Wc;
+  float up_sy, up_sx;   // ATen's align_corners=True scale (in - 1) / (out - 1), fp32
+  float* flow_up;
+  long long fus[3];
   unsigned long long* path_ctr;
   long long* dbg;       // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 192 slots per CTA
 };
@@ -115,6 +131,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (lane = row, 8 consecutive 32-bit columns = the K = 8 tf32 values of one instruction)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait for the loads into v[0..23]; the registers pass through the statement so that no use can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait24(uint32_t* v) {
@@ -126,6 +155,19 @@ __device__ __forceinline__ void tmem_ld_wait24(uint32_t* v) {
   asm volatile("" : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]) : : "memory");
 }
 __device__ __forceinline__ int slot_of(int kc) { return kc & 3; }
+// Every wait carries a suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
+// re-polling.  mbarrier polls are shared-memory operations; with 22 warps of which most are waiting at any time, plain
+// try_wait loops competed with the gather's LDS / STS traffic for the same pipe.
+#ifndef CERB_TC_WAIT_HINT_NS
+#define CERB_TC_WAIT_HINT_NS 20000
+#endif
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
+#if CERB_TC_WAIT_HINT_NS > 0
+  mbar_wait_hint(bar, parity, CERB_TC_WAIT_HINT_NS);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 
 // hi = tf32(v) (round to nearest, low 13 mantissa bits zero), lo = v - hi (exact)
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
@@ -143,13 +185,13 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
   const uint32_t sbase = smem_u32(smem);
   int* red = (int*)(smem + OFF_RED);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
-  uint64_t* a_full = bars;                    // [SLOTS] x1 slot written (4 warps)
+  uint64_t* a_full = bars;                    // [SLOTS] x1 slot written (drain warps 4-7)
   uint64_t* b_full = bars + SLOTS;            // [SLOTS] warped-x2 slot written (12 warps)
   uint64_t* slot_empty = bars + 2 * SLOTS;    // [SLOTS] MMAs reading the slot have retired (tcgen05.commit)
   uint64_t* raw_full = bars + 3 * SLOTS;      // [RS]
   uint64_t* raw_empty = raw_full + RS;        // [RS]
   uint64_t* d_full = raw_empty + RS;          // accumulator of the tile complete
-  uint64_t* d_empty = d_full + 1;             // accumulator drained (4 warps)
+  uint64_t* d_empty = d_full + 1;             // accumulator drained (8 warps)
   uint64_t* bbox_full = d_empty + 1;          // [2] every gather warp has published its share of the tile's tap bounding box
   uint64_t* bbox_empty = bbox_full + 2;       // [2] the TMA warp has read it (the slot may be rewritten two tiles later)
   uint32_t* tmem_slot = (uint32_t*)(smem + OFF_TMEM);
@@ -161,7 +203,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 
   if (tid == 0) {
     for (int s = 0; s < SLOTS; ++s) {
-      mbar_init(&a_full[s], EPI_WARPS);
+      mbar_init(&a_full[s], A_WARPS);
       mbar_init(&b_full[s], GATHER_WARPS);
       mbar_init(&slot_empty[s], 1);
     }
@@ -194,22 +236,26 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
   const int nks = a.nks;
 
   if (warp < EPI_WARPS) {
-    // =========================== x1 staging + accumulator drain: thread = pixel ===========================
-    const int py = tid >> 4, px = tid & 15;
-    const uint32_t arow = (uint32_t)tid * 128u, sw = (uint32_t)(tid & 7);
+    // =========================== x1 operand (warps 4-7) + accumulator drain: thread = pixel ===========================
+    // TMEM lane = pixel, column = halo position; this lane's displacements are halo rows py..py+8, columns px..px+8.
+    // Warps w and w + 4 share a lane quadrant: w takes its halo rows 0-5, w + 4 rows 6-9 and the x1 staging.
+    const int q = warp & 3;
+    const bool a_warp = warp >= A_WARPS;
+    const int pl = q * 32 + lane;                   // pixel of the tile = TMEM lane
+    const int py = pl >> 4, px = pl & 15;
     const float fC = (float)g.C, rC = __frcp_rn((float)g.C);
     const bool c_pow2 = (g.C & (g.C - 1)) == 0;   // 1/C exact: the division is one multiply
     const long long os1 = g.os[1];
-    // x1 values are requested a group of four K steps (32 channels) at a time, in one burst right after the previous
-    // group has been staged: the next tile's first group is in flight while this tile drains.  (Requests interleaved
-    // with the consumption of older ones made every use wait for the youngest load: scoreboards count, they do not
-    // track individual loads.)
-    float nx[SLOTS][KC];
-    auto request_group = [&](int tile, int ks0) {
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    // x1: 32 channels of this thread's pixel are requested in one burst and consumed right away (loads interleaved with
+    // the consumption of older ones made every use wait for the youngest: scoreboards count, they do not track loads)
+    int ka = 0;   // K steps staged so far (all tiles)
+    auto stage_a_group = [&](int tile, int ks0) {
       const int n = tile / per_img, trem = tile - n * per_img;
       const int iy = (trem / a.tiles_x) * TY + a.off + py, ix = (trem % a.tiles_x) * TX + a.off + px;
       const bool inimg = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const T* p = x1 + (long long)n * g.x1s[0] + (long long)min(max(iy, 0), g.H - 1) * g.x1s[2] + min(max(ix, 0), g.W - 1);
+      float nx[SLOTS][KC];
 #pragma unroll
       for (int b = 0; b < SLOTS; ++b)
 #pragma unroll
@@ -218,54 +264,52 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           const float v = ldg_f32(p + (long long)min(ch, g.C - 1) * g.x1s[1]);
           nx[b][c] = (inimg && ch < g.C) ? v : 0.f;
         }
-    };
-    int kc = 0, ti = 0;
-    if ((int)blockIdx.x < a.total_tiles) request_group(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-      const bool has_next = tile + (int)gridDim.x < a.total_tiles;
-      for (int ks4 = 0; ks4 < nks; ks4 += SLOTS) {
 #pragma unroll
-        for (int b = 0; b < SLOTS; ++b) {
-          const int ks = ks4 + b;
-          if (ks < nks) {
-            float hi[KC], lo[KC];
+      for (int b = 0; b < SLOTS; ++b) {
+        if (ks0 + b < nks) {
+          float hi[KC], lo[KC];
 #pragma unroll
-            for (int c = 0; c < KC; ++c) split_tf32(nx[b][c], hi[c], lo[c]);
-            const int slot = kc & (SLOTS - 1), use = kc >> 2;
-            mbar_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
-            const uint32_t c0 = (((uint32_t)(2 * slot)) ^ sw) << 4, c1 = (((uint32_t)(2 * slot + 1)) ^ sw) << 4;
-            sts128(sbase + OFF_AHI + arow + c0, make_float4(hi[0], hi[1], hi[2], hi[3]));
-            sts128(sbase + OFF_AHI + arow + c1, make_float4(hi[4], hi[5], hi[6], hi[7]));
-            sts128(sbase + OFF_ALO + arow + c0, make_float4(lo[0], lo[1], lo[2], lo[3]));
-            sts128(sbase + OFF_ALO + arow + c1, make_float4(lo[4], lo[5], lo[6], lo[7]));
-            fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[slot]);
-            if (tid == 0 && ks < 4) TC_TRACE(ti, 26 + ks);
-            ++kc;
-          }
+          for (int c = 0; c < KC; ++c) split_tf32(nx[b][c], hi[c], lo[c]);
+          const int slot = ka & (SLOTS - 1), use = ka >> 2;
+          tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+          tc_fence_after();
+          tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u, hi);
+          tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u + 8u, lo);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[slot]);
+          ++ka;
         }
-        if (ks4 + SLOTS < nks) request_group(tile, ks4 + SLOTS);
-        else if (has_next) request_group(tile + gridDim.x, 0);
       }
-      // ---- drain: TMEM lane = pixel, column = halo position; this lane's displacements are rows py..py+8, columns px..px+8
+    };
+    int ti = 0;
+    if (a_warp && (int)blockIdx.x < a.total_tiles) stage_a_group(blockIdx.x, 0);   // first group of the first tile
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      if (a_warp) {
+        // the rest of this tile's x1 (slots free up as its MMAs retire), then the first group of the next tile: staged
+        // while this tile's MMAs run, so the next tile's can start the moment the accumulator has drained
+        for (int ks0 = SLOTS; ks0 < nks; ks0 += SLOTS) stage_a_group(tile, ks0);
+        if (tile + (int)gridDim.x < a.total_tiles) stage_a_group(tile + gridDim.x, 0);
+        if (warp == A_WARPS && lane == 0) TC_TRACE(ti, 26);
+      }
       const int n = tile / per_img, trem = tile - n * per_img;
       const int oy = (trem / a.tiles_x) * TY + py, ox = (trem % a.tiles_x) * TX + px;
       const bool pix_ok = oy < g.outH && ox < g.outW;
       T* op = (T*)a.out + (long long)n * g.os[0] + (long long)min(oy, g.outH - 1) * g.os[2] + min(ox, g.outW - 1);
-      mbar_wait(d_full, (uint32_t)(ti & 1));
+      tc_wait(d_full, (uint32_t)(ti & 1));
       tc_fence_after();
       if (tid == 0) TC_TRACE(ti, 30);
-      const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+      const int rr0 = a_warp ? 6 : 0, rr1 = a_warp ? 10 : 6;
 #pragma unroll 1
-      for (int rr = 0; rr < 10; ++rr) {
+      for (int rr = rr0; rr < rr1; ++rr) {
         uint32_t v[24];
-        const uint32_t col = (uint32_t)((2 * warp + rr) * HX);
+        const uint32_t col = (uint32_t)((2 * q + rr) * HX);
         tmem_ld8(tlane + col, v);
         tmem_ld8(tlane + col + 8, v + 8);
         tmem_ld8(tlane + col + 16, v + 16);
         tmem_ld_wait24(v);
-        if (rr == 9) {   // every load of the tile has landed: the next tile's MMAs may overwrite the accumulator
+        if (rr == rr1 - 1) {   // every load of this warp has landed: (with the other seven) the next tile's MMAs may start
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(d_empty);
@@ -279,7 +323,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         for (int i = 0; i < 10; ++i) v[i] = (px & 2) ? v[i + 2] : v[i];
 #pragma unroll
         for (int i = 0; i < 9; ++i) v[i] = (px & 1) ? v[i + 1] : v[i];
-        const int dy = rr - (py & 1);   // halo row 2w + rr is displacement row (2w + rr) - py of this pixel
+        const int dy = rr - (py & 1);   // halo row 2q + rr is displacement row (2q + rr) - py of this pixel
         if (pix_ok && dy >= 0 && dy <= 2 * MD) {
           T* orow = op + (long long)(dy * (2 * MD + 1)) * os1;
 #pragma unroll
@@ -298,7 +342,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     const int gt = tid - EPI_WARPS * 32, gw = warp - EPI_WARPS;
     const int hy = gt / HX, hx = gt - hy * HX;
     const uint32_t brow = (uint32_t)gt * 128u, sw = (uint32_t)(gt & 7);
-    const bool warped = a.flow != nullptr;
+    const bool upflow = a.cflow != nullptr;
+    const bool warped = a.flow != nullptr || upflow;
     const AxisConst axis_x = make_axis(g.W), axis_y = make_axis(g.H);
     // sampling data of one tile for this thread's halo position
     struct Pos {
@@ -316,9 +361,45 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     };
     auto load_flow = [&](int tile, float& fu, float& fv) {
       int n, cy, cx;
-      locate(tile, n, cy, cx);
-      const float* fp = a.flow + (long long)n * g.fls[0] + (long long)cy * g.fls[2] + cx;
-      fu = __ldg(fp); fv = __ldg(fp + g.fls[1]);
+      const bool inside = locate(tile, n, cy, cx);
+      if (!upflow) {
+        const float* fp = a.flow + (long long)n * g.fls[0] + (long long)cy * g.fls[2] + cx;
+        fu = __ldg(fp); fv = __ldg(fp + g.fls[1]);
+        return;
+      }
+      // flow = interpolate(2 * coarse, scale_factor=2, bilinear, align_corners=True) (pwcnet_sfd.py:176), evaluated per
+      // halo position with ATen's arithmetic (upsample_bilinear2d: src = scale * dst, lambda = src - int(src)); doubling
+      // commutes exactly with the blend.  Same expressions as costvolume_fwd.cu: bit-exact against ATen's CUDA kernel.
+      const float* cn = a.cflow + (long long)n * a.cfs[0];
+      const float h1r = __fmul_rn(a.up_sy, (float)cy), w1r = __fmul_rn(a.up_sx, (float)cx);
+      const int h1 = (int)h1r, w1 = (int)w1r;
+      const int h1p = (h1 < a.Hc - 1) ? 1 : 0, w1p = (w1 < a.Wc - 1) ? 1 : 0;
+      const float h1l = __fsub_rn(h1r, (float)h1), w1l = __fsub_rn(w1r, (float)w1);
+      const float h0l = __fsub_rn(1.f, h1l), w0l = __fsub_rn(1.f, w1l);
+      const float* p0 = cn + (long long)h1 * a.cfs[2] + w1;
+      const float* p1 = p0 + (long long)h1p * a.cfs[2];
+      float cv[8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        cv[4 * c + 0] = __ldg(p0 + c * a.cfs[1]);
+        cv[4 * c + 1] = __ldg(p0 + c * a.cfs[1] + w1p);
+        cv[4 * c + 2] = __ldg(p1 + c * a.cfs[1]);
+        cv[4 * c + 3] = __ldg(p1 + c * a.cfs[1] + w1p);
+      }
+      float r[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float t0 = __fmaf_rn(w0l, cv[4 * c + 0], __fmul_rn(w1l, cv[4 * c + 1]));
+        const float t1 = __fmaf_rn(w0l, cv[4 * c + 2], __fmul_rn(w1l, cv[4 * c + 3]));
+        r[c] = __fmul_rn(2.f, __fmaf_rn(h0l, t0, __fmul_rn(h1l, t1)));
+      }
+      fu = r[0]; fv = r[1];
+      // positions inside the tile itself (each pixel of the image exactly once) also write the up-sampled flow out
+      if (inside && hy >= g.md && hy < g.md + TY && hx >= g.md && hx < g.md + TX) {
+        float* up = a.flow_up + (long long)n * a.fus[0] + (long long)cy * a.fus[2] + cx;
+        up[0] = r[0];
+        up[a.fus[1]] = r[1];
+      }
     };
     // taps of the tile and this warp's share of their bounding box (published for tile iteration `it`)
     auto prepare = [&](int tile, int it, float fu, float fv) -> Pos {
@@ -343,7 +424,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
         ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
         if (lane == 0) {
-          if (it >= 2) mbar_wait(&bbox_empty[it & 1], (uint32_t)(((it >> 1) - 1) & 1));
+          if (it >= 2) tc_wait(&bbox_empty[it & 1], (uint32_t)(((it >> 1) - 1) & 1));
           int* rp = red + (it & 1) * (GATHER_WARPS * 4) + gw * 4;
           *reinterpret_cast<int4*>(rp) = make_int4(xmin, xmax, ymin, ymax);
           mbar_arrive(&bbox_full[it & 1]);
@@ -370,7 +451,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       // ---- does the tile's sampling footprint fit the raw box?
       int path = PATH_DIRECT, ox = 0, oy = 0;
       if (a.use_raw) {
-        mbar_wait(&bbox_full[ti & 1], (uint32_t)((ti >> 1) & 1));
+        tc_wait(&bbox_full[ti & 1], (uint32_t)((ti >> 1) & 1));
         const int4* rp = reinterpret_cast<const int4*>(red + (ti & 1) * (GATHER_WARPS * 4));
         int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
 #pragma unroll
@@ -392,44 +473,72 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       // the operand slot of this K step is free and written: publish it
       auto stage_b = [&](const float (&hi)[KC], const float (&lo)[KC], int ks) {
         const int slot = kc & (SLOTS - 1), use = kc >> 2;
-        mbar_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+        tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
         if (gt == 0 && ks < 4) TC_TRACE(ti, 4 + 3 * ks);
         const uint32_t c0 = (((uint32_t)(2 * slot)) ^ sw) << 4, c1 = (((uint32_t)(2 * slot + 1)) ^ sw) << 4;
         sts128(sbase + OFF_BHI + brow + c0, make_float4(hi[0], hi[1], hi[2], hi[3]));
         sts128(sbase + OFF_BHI + brow + c1, make_float4(hi[4], hi[5], hi[6], hi[7]));
         sts128(sbase + OFF_BLO + brow + c0, make_float4(lo[0], lo[1], lo[2], lo[3]));
         sts128(sbase + OFF_BLO + brow + c1, make_float4(lo[4], lo[5], lo[6], lo[7]));
-        fence_proxy_async_smem();
-        __syncwarp();
       };
       if (path == PATH_RAW) {
         // byte offsets of the four taps inside a channel plane of the box (positions without a sample read offset 0)
         const int r0 = (cur.y0 - oy) * RAW_W - ox, r1 = (cur.y1c - oy) * RAW_W - ox;
         const uint32_t t0 = valid ? (uint32_t)(r0 + cur.x0) << 2 : 0u, t1 = valid ? (uint32_t)(r0 + cur.x1c) << 2 : 0u;
         const uint32_t t2 = valid ? (uint32_t)(r1 + cur.x0) << 2 : 0u, t3 = valid ? (uint32_t)(r1 + cur.x1c) << 2 : 0u;
+        // Software pipeline over half K steps (4 channels = one 16-byte operand chunk): the 16 tap loads of the next half
+        // step -- across the K-step boundary too, the box is usually there already -- are in flight while this one is
+        // blended, split and stored.  Without it the gather warps, which the barriers keep in lockstep, all load, then all
+        // compute, then all store, and the shared-memory pipe idles half of the time.
+        auto load_half = [&](uint32_t rb, int half, float (&dst)[4][4]) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t pl = rb + (uint32_t)(half * 4 + c) * RAW_PLANE;
+            dst[c][0] = lds_f32(pl + t0);
+            dst[c][1] = lds_f32(pl + t1);
+            dst[c][2] = lds_f32(pl + t2);
+            dst[c][3] = lds_f32(pl + t3);
+          }
+        };
+        auto blend_half = [&](const float (&v)[4][4], float4& hi, float4& lo) {
+          float h[4], l[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_tf32(valid ? blend(v[c][0], v[c][1], v[c][2], v[c][3], tp) : 0.f, h[c], l[c]);
+          hi = make_float4(h[0], h[1], h[2], h[3]);
+          lo = make_float4(l[0], l[1], l[2], l[3]);
+        };
+        float la[4][4], lb[4][4];
+        {
+          const int rs = rc % RS, ruse = rc / RS;
+          tc_wait(&raw_full[rs], (uint32_t)(ruse & 1));
+          load_half(sbase + OFF_RAW + (uint32_t)rs * RAW_STAGE, 0, la);
+        }
         for (int ks = 0; ks < nks; ++ks, ++kc, ++rc) {
-          const int rs = rc & (RS - 1), ruse = rc / RS;
-          mbar_wait(&raw_full[rs], (uint32_t)(ruse & 1));
-          if (gt == 0 && ks < 4) TC_TRACE(ti, 3 + 3 * ks);
+          const int rs = rc % RS;
           const uint32_t rb = sbase + OFF_RAW + (uint32_t)rs * RAW_STAGE;
-          float tv[KC][4];
-#pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            tv[c][0] = lds_f32(rb + t0 + (uint32_t)c * RAW_PLANE);
-            tv[c][1] = lds_f32(rb + t1 + (uint32_t)c * RAW_PLANE);
-            tv[c][2] = lds_f32(rb + t2 + (uint32_t)c * RAW_PLANE);
-            tv[c][3] = lds_f32(rb + t3 + (uint32_t)c * RAW_PLANE);
+          if (gt == 0 && ks < 4) TC_TRACE(ti, 3 + 3 * ks);
+          load_half(rb, 1, lb);
+          float4 hi, lo;
+          blend_half(la, hi, lo);
+          const int slot = kc & (SLOTS - 1), use = kc >> 2;
+          tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+          if (gt == 0 && ks < 4) TC_TRACE(ti, 4 + 3 * ks);
+          const uint32_t c0 = (((uint32_t)(2 * slot)) ^ sw) << 4, c1 = (((uint32_t)(2 * slot + 1)) ^ sw) << 4;
+          sts128(sbase + OFF_BHI + brow + c0, hi);
+          sts128(sbase + OFF_BLO + brow + c0, lo);
+          if (ks + 1 < nks) {   // first half of the next K step
+            const int rn = (rc + 1) % RS, rnuse = (rc + 1) / RS;
+            tc_wait(&raw_full[rn], (uint32_t)(rnuse & 1));
+            load_half(sbase + OFF_RAW + (uint32_t)rn * RAW_STAGE, 0, la);
           }
-          float hi[KC], lo[KC];
-#pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            const float r = valid ? blend(tv[c][0], tv[c][1], tv[c][2], tv[c][3], tp) : 0.f;
-            split_tf32(r, hi[c], lo[c]);
-          }
-          stage_b(hi, lo, ks);
+          blend_half(lb, hi, lo);
+          sts128(sbase + OFF_BHI + brow + c1, hi);
+          sts128(sbase + OFF_BLO + brow + c1, lo);
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+          __syncwarp();
           if (lane == 0) {
             mbar_arrive(&raw_empty[rs]);
-            mbar_arrive(&b_full[slot_of(kc)]);
+            mbar_arrive(&b_full[slot]);
           }
           if (gt == 0 && ks < 4) TC_TRACE(ti, 5 + 3 * ks);
           if (ks == 0 && has_next) nxt = prepare(tile + gridDim.x, ti + 1, nfu, nfv);
@@ -457,6 +566,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
             split_tf32(r, hi[c], lo[c]);
           }
           stage_b(hi, lo, ks);
+          fence_proxy_async_smem();
+          __syncwarp();
           if (lane == 0) mbar_arrive(&b_full[slot_of(kc)]);
           if (ks == 0 && has_next) nxt = prepare(tile + gridDim.x, ti + 1, nfu, nfv);
         }
@@ -468,28 +579,28 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     if (lane == 0) {
       // instruction descriptor: D fp32, A / B tf32, both K-major, N = 192, M = 128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-      const uint64_t d_ah = make_desc(sbase + OFF_AHI), d_al = make_desc(sbase + OFF_ALO);
       const uint64_t d_bh0 = make_desc(sbase + OFF_BHI), d_bh1 = make_desc(sbase + OFF_BHI + NH * 128);
       const uint64_t d_bl0 = make_desc(sbase + OFF_BLO), d_bl1 = make_desc(sbase + OFF_BLO + NH * 128);
       int kc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        mbar_wait(d_empty, (uint32_t)((ti & 1) ^ 1));   // previous tile drained
+        tc_wait(d_empty, (uint32_t)((ti & 1) ^ 1));   // previous tile drained
         tc_fence_after();
         TC_TRACE(ti, 20);
         for (int ks = 0; ks < nks; ++ks, ++kc) {
           const int slot = kc & (SLOTS - 1), use = kc >> 2;
-          mbar_wait(&a_full[slot], (uint32_t)(use & 1));
-          mbar_wait(&b_full[slot], (uint32_t)(use & 1));
+          tc_wait(&a_full[slot], (uint32_t)(use & 1));
+          tc_wait(&b_full[slot], (uint32_t)(use & 1));
           tc_fence_after();
           if (ks < 4) TC_TRACE(ti, 21 + ks);
           const uint64_t ko = (uint64_t)(2 * slot);   // 32 bytes per K step inside the 128-byte swizzle atom
           const uint32_t acc = ks > 0 ? 1u : 0u;
-          umma_tf32(tmem, d_ah + ko, d_bh0 + ko, idesc, acc);
-          umma_tf32(tmem, d_al + ko, d_bh0 + ko, idesc, 1u);
-          umma_tf32(tmem, d_ah + ko, d_bl0 + ko, idesc, 1u);
-          umma_tf32(tmem + NH, d_ah + ko, d_bh1 + ko, idesc, acc);
-          umma_tf32(tmem + NH, d_al + ko, d_bh1 + ko, idesc, 1u);
-          umma_tf32(tmem + NH, d_ah + ko, d_bl1 + ko, idesc, 1u);
+          const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
+          umma_tf32_ta(tmem, a_hi, d_bh0 + ko, idesc, acc);
+          umma_tf32_ta(tmem, a_lo, d_bh0 + ko, idesc, 1u);
+          umma_tf32_ta(tmem, a_hi, d_bl0 + ko, idesc, 1u);
+          umma_tf32_ta(tmem + NH, a_hi, d_bh1 + ko, idesc, acc);
+          umma_tf32_ta(tmem + NH, a_lo, d_bh1 + ko, idesc, 1u);
+          umma_tf32_ta(tmem + NH, a_hi, d_bl1 + ko, idesc, 1u);
           umma_commit(&slot_empty[slot]);
         }
         umma_commit(d_full);
@@ -503,7 +614,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       int rc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
         const int n = tile / per_img;
-        mbar_wait(&bbox_full[ti & 1], (uint32_t)((ti >> 1) & 1));
+        tc_wait(&bbox_full[ti & 1], (uint32_t)((ti >> 1) & 1));
         TC_TRACE(ti, 15);
         const int4* rp = reinterpret_cast<const int4*>(red + (ti & 1) * (GATHER_WARPS * 4));
         int xmin = 0x7fffffff, xmax = -0x7fffffff, ymin = 0x7fffffff, ymax = -0x7fffffff;
@@ -517,8 +628,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         const int ox = xmin & ~3, oy = ymin;
         if (xmin <= xmax && xmax - ox < RAW_W && ymax - oy < RAW_H) {
           for (int ks = 0; ks < nks; ++ks, ++rc) {
-            const int rs = rc & (RS - 1), ruse = rc / RS;
-            mbar_wait(&raw_empty[rs], (uint32_t)((ruse & 1) ^ 1));
+            const int rs = rc % RS, ruse = rc / RS;
+            tc_wait(&raw_empty[rs], (uint32_t)((ruse & 1) ^ 1));
             mbar_arrive_expect_tx(&raw_full[rs], RAW_STAGE);
             tma_load_4d(smem + OFF_RAW + (uint32_t)rs * RAW_STAGE, &tm_raw, &raw_full[rs], ox, oy, ks * KC, x2_item(g, n));
             if (ks < 4) TC_TRACE(ti, 16 + ks);
@@ -541,12 +652,13 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 }  // namespace tc
 
 bool tc_forward_supported(const Geom& g, int dtype, const UpFlow* uf) {
-  return dtype == CERB_F32 && uf == nullptr && g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == tc::MD && g.outH > 0 && g.outW > 0;
+  if (uf != nullptr && (g.pad != g.md || (g.H & 1) || (g.W & 1))) return false;   // tiles must cover the image exactly once
+  return dtype == CERB_F32 && g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == tc::MD && g.outH > 0 && g.outW > 0;
 }
 
 cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
-                                        cudaStream_t stream) {
-  if (!tc_forward_supported(g, dtype, nullptr)) return cudaErrorNotSupported;
+                                        cudaStream_t stream, const UpFlow* uf) {
+  if (!tc_forward_supported(g, dtype, uf)) return cudaErrorNotSupported;
   tc::Args a;
   a.g = g;
   a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out;
@@ -557,10 +669,19 @@ cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1
   a.nks = (g.C + tc::KC - 1) / tc::KC;
   a.path_ctr = get_path_counters();
   a.dbg = get_trace_buffer();
+  a.cflow = nullptr; a.flow_up = nullptr; a.Hc = a.Wc = 0; a.up_sy = a.up_sx = 0.f;
+  for (int i = 0; i < 3; ++i) a.cfs[i] = a.fus[i] = 0;
+  if (uf != nullptr) {
+    a.cflow = uf->coarse; a.flow_up = uf->up; a.Hc = uf->Hc; a.Wc = uf->Wc;
+    for (int i = 0; i < 3; ++i) { a.cfs[i] = uf->cs[i]; a.fus[i] = uf->us[i]; }
+    // ATen area_pixel_compute_scale<float>(in, out, align_corners=true): (float)(in - 1) / (out - 1)
+    a.up_sy = g.H > 1 ? (float)(uf->Hc - 1) / (float)(g.H - 1) : 0.f;
+    a.up_sx = g.W > 1 ? (float)(uf->Wc - 1) / (float)(g.W - 1) : 0.f;
+  }
   CUtensorMap tm_raw;
   memset(&tm_raw, 0, sizeof(tm_raw));
   a.use_raw = 0;
-  if (!getenv("CERB_DEBUG_TC_NO_RAW"))
+  if (!getenv("CERB_DEBUG_TC_NO_RAW"))   // TMA needs 16-byte aligned base / strides (make_tmap_nchw checks)
     a.use_raw = make_tmap_nchw(&tm_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, tc::RAW_W, tc::RAW_H,
                                tc::KC, false) ? 1 : 0;
   auto kern = tc::warp_corr_fwd_tc_kernel<float>;

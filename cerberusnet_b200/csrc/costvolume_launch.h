@@ -36,7 +36,7 @@ cudaError_t launch_warp_corr_forward(const Geom& g, int dtype, const void* x1, c
 // tensor-core forward (costvolume_fwd_tc.cu)
 bool tc_forward_supported(const Geom& g, int dtype, const UpFlow* upflow);
 cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
-                                        cudaStream_t stream);
+                                        cudaStream_t stream, const UpFlow* upflow = nullptr);
 
 // workspace: fp32 [B,C,H,W] accumulation buffer for grad_x2 when dtype is 16-bit and flow != NULL
 cudaError_t launch_warp_corr_backward(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow,

@@ -22,7 +22,7 @@ from oracle import c_oracle as co
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
-VARIANTS = [0, 1, 2, 3, 4, 5]
+VARIANTS = [0, 1, 2, 3, 4, 5, 7]   # 7: tensor-core (tcgen05 / TMEM, 3xTF32) forward
 
 
 def dev():
@@ -599,8 +599,12 @@ def test_many_tiles_per_cta_persistent_loop(dtype, tol, md):
         ref = to.level_forward(a, b, f, 4, 1, 4, 1, 1, to.WARP_TORCH, 0.1)
         g = torch.randn_like(ref)
         ref.backward(g)
+        # (the saved activation the backward masks with is the reference forward's: an output within rounding of zero
+        # may come out with the other sign from a kernel that sums in a different order, and one flipped mask bit moves
+        # a gradient element by (1 - slope) |g x| / C -- the forward's own parity is asserted above)
         out = ops.warp_corr_forward(x1[:1], x2[:1], fl[:1], 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
-        g1, g2, gf = ops.warp_corr_backward(x1[:1], x2[:1], fl[:1], out, g, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
+        assert rel_err(out.cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+        g1, g2, gf = ops.warp_corr_backward(x1[:1], x2[:1], fl[:1], ref.detach(), g, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
         for ours, theirs in ((g1, a.grad), (g2, b.grad), (gf, f.grad)):
             assert rel_err(ours.cpu().numpy(), theirs.cpu().numpy()) < 2 * TOL
 

@@ -168,22 +168,29 @@ def test_large_flow_variation_uses_the_large_raw_box():
     x1, x2 = torch.randn(B, C, H, W, device=dev()), torch.randn(B, C, H, W, device=dev())
     coarse = torch.randn(B, 2, H // 2, W // 2, device=dev()) * 2.5
     fl = torch.nn.functional.interpolate(coarse * 2, scale_factor=2, mode="bilinear", align_corners=True)
-    ctr = torch.zeros(4, dtype=torch.int64, device=dev())
     L = cb.lib()
-    L.cerb_debug_set_path_counters(ctypes.c_void_p(ctr.data_ptr()))
-    try:
-        out = ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1)
-        torch.cuda.synchronize()
-    finally:
-        L.cerb_debug_set_path_counters(None)
-    small, direct, large = int(ctr[1]), int(ctr[2]), int(ctr[3])
+
+    def run(variant):
+        ctr = torch.zeros(4, dtype=torch.int64, device=dev())
+        L.cerb_debug_set_path_counters(ctypes.c_void_p(ctr.data_ptr()))
+        try:
+            o = ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=variant)
+            torch.cuda.synchronize()
+        finally:
+            L.cerb_debug_set_path_counters(None)
+        return o, int(ctr[1]), int(ctr[2]), int(ctr[3])
+
+    out, small, direct, large = run(1)   # CUDA-core kernel, 8x32 tiles
     assert small + direct + large == 128
     assert large > 0 and direct <= 2, (small, large, direct)
+    out_tc, raw_tc, direct_tc, _ = run(7)   # tensor-core kernel, 8x16 tiles: one box size, the rest gathers from global memory
+    assert raw_tc + direct_tc == 256 and raw_tc > 0
     ref = ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=5)   # generic kernel (pinned to the oracle elsewhere)
     assert rel_err(out.cpu().numpy(), ref.cpu().numpy()) < TOL
-    s = slice(0, 1)
+    assert rel_err(out_tc.cpu().numpy(), ref.cpu().numpy()) < TOL
     ref_o = co.level_forward(x1.cpu().numpy(), x2.cpu().numpy(), fl.cpu().numpy(), 4, 1, 4, 1, 1, co.WARP_TORCH, 0.1)
     assert rel_err(out.cpu().numpy(), ref_o) < TOL
+    assert rel_err(out_tc.cpu().numpy(), ref_o) < TOL
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float16, 6e-4), (torch.bfloat16, 5e-3)])
