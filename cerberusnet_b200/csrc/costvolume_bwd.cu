@@ -648,25 +648,43 @@ static int grid_for(long long total, int block) {
   return (int)b;
 }
 
+// per-device opt-in to > 48 KB of dynamic shared memory (function attributes are per device: one process may drive several GPUs)
+template <typename K>
+static cudaError_t ensure_smem_attr(K kern, size_t smem, unsigned long long& devs) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+  if (bit != 0ull && (devs & bit)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) devs |= bit;
+  return e;
+}
+
 template <typename T, int TYB>
 static cudaError_t launch_tiled_pair(BwdArgs& a, const Geom& g, cudaStream_t stream) {
   using Cfg = BwdCfg<TYB>;
   a.tiles_y = (g.H + TYB - 1) / TYB;
   dim3 grid(a.tiles_x, a.tiles_y, g.B);
-  // function attributes are per device (one process may drive several GPUs): remember which have the opt-in
-  static unsigned long long attr_devs = 0ull;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
-  if (bit == 0ull || !(attr_devs & bit)) {
-    cudaError_t e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 0, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(corr_bwd_tiled_kernel<T, 1, TYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e != cudaSuccess) return e;
-    attr_devs |= bit;
-  }
+  static unsigned long long devs0 = 0ull, devs1 = 0ull;
+  cudaError_t e = ensure_smem_attr(corr_bwd_tiled_kernel<T, 0, TYB>, Cfg::SMEM, devs0);
+  if (e != cudaSuccess) return e;
+  e = ensure_smem_attr(corr_bwd_tiled_kernel<T, 1, TYB>, Cfg::SMEM, devs1);
+  if (e != cudaSuccess) return e;
   corr_bwd_tiled_kernel<T, 0, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
   corr_bwd_tiled_kernel<T, 1, TYB><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
+  return cudaSuccess;
+}
+
+// both gradients of a tile in one CTA; with SPLAT the gradient with respect to the warped map never leaves the chip
+template <typename T, typename GT, int TYB, bool SPLAT>
+static cudaError_t launch_tiled_fused(BwdArgs& a, const Geom& g, cudaStream_t stream) {
+  using Cfg = BwdCfg<TYB>;
+  a.tiles_y = (g.H + TYB - 1) / TYB;
+  dim3 grid(a.tiles_x, a.tiles_y, g.B);
+  static unsigned long long devs = 0ull;
+  cudaError_t e = ensure_smem_attr(corr_bwd_fused_kernel<T, GT, TYB, SPLAT>, Cfg::SMEM, devs);
+  if (e != cudaSuccess) return e;
+  corr_bwd_fused_kernel<T, GT, TYB, SPLAT><<<grid, Cfg::NT, Cfg::SMEM, stream>>>(a);
   return cudaSuccess;
 }
 
@@ -710,7 +728,40 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
                      (a.s_hs[w] % 4) == 0 && (g.md % 4) == 0 && (g.W % 4) == 0;
     a.tiles_x = (g.W + BT_X - 1) / BT_X;
     static const int force_ty = getenv("CERB_DEBUG_BWD_TY") ? atoi(getenv("CERB_DEBUG_BWD_TY")) : 0;
+    static const bool unfused = getenv("CERB_DEBUG_BWD_UNFUSED") != nullptr;
     const bool ty4 = force_ty ? force_ty == 4 : true;
+    if (!unfused && ty4) {
+      // one kernel for both gradients.  With a flow the second one is splatted through the bilinear taps straight into
+      // grad_x2 (zeroed here; 16-bit: an fp32 accumulator in the workspace, narrowed once) and reduced into grad_flow
+      // inside that kernel: no gradient-of-the-warped-map workspace, no separate warp-backward pass.
+      a.x2 = x2; a.flow = flow; a.gflow = gflow;
+      if (flow == nullptr) {
+        a.gx2 = nullptr;
+        e = launch_tiled_fused<T, T, 4, false>(a, g, stream);
+        if (e != cudaSuccess) return e;
+        count_launches(1);
+        return cudaGetLastError();
+      }
+      if (sizeof(T) == 2) {
+        float* acc32 = reinterpret_cast<float*>(gwarped + in_elems);
+        e = cudaMemsetAsync(acc32, 0, (size_t)in_elems * sizeof(float), stream);
+        if (e != cudaSuccess) return e;
+        a.gx2 = acc32;
+        e = launch_tiled_fused<T, float, 4, true>(a, g, stream);
+        if (e != cudaSuccess) return e;
+        cvt_from_f32_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(acc32, (T*)gx2, in_elems);
+        count_launches(4);
+      } else {
+        e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
+        if (e != cudaSuccess) return e;
+        a.gx2 = gx2;
+        e = launch_tiled_fused<T, T, 4, true>(a, g, stream);
+        if (e != cudaSuccess) return e;
+        count_launches(3);
+      }
+      return cudaGetLastError();
+    }
+    a.x2 = nullptr; a.flow = nullptr; a.gx2 = nullptr; a.gflow = nullptr;
     e = ty4 ? launch_tiled_pair<T, 4>(a, g, stream) : launch_tiled_pair<T, 8>(a, g, stream);
     if (e != cudaSuccess) return e;
     if (flow != nullptr) {

@@ -301,20 +301,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       tc_fence_after();
       if (tid == 0) TC_TRACE(ti, 30);
       const int rr0 = a_warp ? 6 : 0, rr1 = a_warp ? 10 : 6;
-#pragma unroll 1
-      for (int rr = rr0; rr < rr1; ++rr) {
-        uint32_t v[24];
-        const uint32_t col = (uint32_t)((2 * q + rr) * HX);
-        tmem_ld8(tlane + col, v);
-        tmem_ld8(tlane + col + 8, v + 8);
-        tmem_ld8(tlane + col + 16, v + 16);
-        tmem_ld_wait24(v);
-        if (rr == rr1 - 1) {   // every load of this warp has landed: (with the other seven) the next tile's MMAs may start
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d_empty);
-          if (tid == 0) TC_TRACE(ti, 31);
-        }
+      // two halo rows per iteration: their select networks and stores are independent instruction streams (one warp
+      // per sub-partition drains at a time -- what it lacks is instruction-level parallelism, not issue slots)
+      auto finish_row = [&](uint32_t (&v)[24], int rr) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = (px & 8) ? v[i + 8] : v[i];
 #pragma unroll
@@ -334,6 +323,27 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
             orow += os1;
           }
         }
+      };
+#pragma unroll 1
+      for (int rr = rr0; rr < rr1; rr += 2) {
+        uint32_t v0[24], v1[24];
+        const uint32_t col = (uint32_t)((2 * q + rr) * HX);
+        tmem_ld8(tlane + col, v0);
+        tmem_ld8(tlane + col + 8, v0 + 8);
+        tmem_ld8(tlane + col + 16, v0 + 16);
+        tmem_ld8(tlane + col + HX, v1);
+        tmem_ld8(tlane + col + HX + 8, v1 + 8);
+        tmem_ld8(tlane + col + HX + 16, v1 + 16);
+        tmem_ld_wait24(v0);
+        tmem_ld_wait24(v1);
+        if (rr == rr1 - 2) {   // every load of this warp has landed: (with the other seven) the next tile's MMAs may start
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d_empty);
+          if (tid == 0) TC_TRACE(ti, 31);
+        }
+        finish_row(v0, rr);
+        finish_row(v1, rr + 1);
       }
       if (tid == 0) TC_TRACE(ti, 32);
     }
