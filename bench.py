@@ -50,7 +50,7 @@ DIRS = 2      # flow directions per step (forward and backward flow of the pair)
 N_SETS = 6    # 6 x 58.7 MB of inputs+outputs = 352 MB > 2 x 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the finest-level kernel (both directions), from this
 # round's `ncu --set full` capture summarised in profiles/r02_ncu_fwd_finest_level.txt
-NCU_TRAFFIC_BYTES_FINEST = None
+NCU_TRAFFIC_BYTES_FINEST = 9238016   # 9.236 MB read + 2 KB written (the 21.2 MB of output is still dirty in L2 at kernel end)
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_fwd_finest_level.txt"
 
 
@@ -558,6 +558,7 @@ def main_gpu(args, rank, world, local_rank):
                           "us_per_launch": round(us, 3), "algorithmic_MB": round(byts / 1e6, 3),
                           "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm_peak, 4),
                           "fp32_TFLOPs": round(fl / us / 1e6, 2), "fma_frac": round(fl / us / 1e6 / fma_peak, 4),
+                          "kernel": "tensor-core (tcgen05, 8x16 tiles)" if (wp and B * ((H + 7) // 8) * ((W + 15) // 16) >= 64) else "CUDA-core (cluster-split 4x16 / 8x16 tiles)",
                           "tiles_small_box": c[1], "tiles_large_box": c[3], "tiles_fallback_direct_gather": c[2],
                           "fallback_rate": round(c[2] / tiles, 4) if wp else 0.0})
         return stats
@@ -577,8 +578,14 @@ def main_gpu(args, rank, world, local_rank):
     roofline = {
         "bound": "hbm", "achieved": dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
         "traffic": NCU_TRAFFIC_BYTES_FINEST, "traffic_source": NCU_TRAFFIC_SOURCE, "peak_source": peak_src,
-        "kernel": f"warp_corr_fwd_kernel<float,8,32,1,4,3> level {dom['level']} (C={dom['C']}, {dom['H']}x{dom['W']}, "
-                  f"{DIRS} flow directions per launch)",
+        "kernel": f"warp_corr_fwd_tc_kernel<float> (tcgen05.mma.kind::tf32 into TMEM, 3xTF32 split of the fp32 operands; 8x16 tiles "
+                  f"as 128x384 Gram tiles) level {dom['level']} (C={dom['C']}, {dom['H']}x{dom['W']}, {DIRS} flow directions per launch)",
+        "tensor_pipe": {"tiles_per_launch": DIRS * ((dom["H"] + 7) // 8) * ((dom["W"] + 15) // 16),
+                        "mma_per_tile": 6 * ((dom["C"] + 7) // 8), "mma_shape": "M128 N192 K8 tf32",
+                        "issued_tf32_TFLOPs": round(DIRS * ((dom["H"] + 7) // 8) * ((dom["W"] + 15) // 16) * 6 * ((dom["C"] + 7) // 8)
+                                                    * 2 * 128 * 192 * 8 / dom["us_per_launch"] / 1e6, 1),
+                        "useful_fraction_of_gram_tile": round(81 / 384, 3),
+                        "note": "not the binding roof: shared-memory bandwidth (tap gather + operand stores + MMA operand reads + raw-box TMA writes) is, see DESIGN 4.1b"},
         "algorithmic_bytes_per_launch": int(dom["algorithmic_MB"] * 1e6),
         "algorithmic_bytes_formula": "directions * H*W*4*(2C + 81 + 2) (SURVEY 8d per direction)",
         "avg_launch_us": dom["us_per_launch"],

@@ -18,7 +18,10 @@
  *     or a negative CERB_E* code for argument errors.  Nothing aborts or throws
  *     (reference: AT_ERROR -> RuntimeError, correlation_cuda.cpp:22-23; NV_CUDA_CHECK ->
  *     abort(), trt_plugins/trt_utils.hpp:7-15);
- *   - thread-safe: no mutable global state.
+ *   - thread-safety: entry points may be called concurrently from several host threads / on several devices.  The only
+ *     process-wide state is lazily initialised and idempotent (per-device function attributes and SM counts, the driver
+ *     entry point of cuTensorMapEncodeTiled, a launch counter updated atomically).  The cerb_debug_* hooks (trace
+ *     buffer, path counters) are global switches for single-threaded debugging and are NOT thread-safe.
  */
 #ifndef CERBERUS_COSTVOLUME_H_
 #define CERBERUS_COSTVOLUME_H_
@@ -105,8 +108,10 @@ CERB_API int cerb_warp_corr_forward(const cerb_corr_params* p, const void* x1, c
 /* Testing / tuning hook: same as cerb_warp_corr_forward with the kernel variant pinned.
  * variant: 0 auto (what cerb_warp_corr_forward uses), 1 8x32-tile kernel with TMA staging,
  * 2 same without TMA (LDG/STG staging), 3 4x16-tile split-channel kernel with TMA, 4 same
- * without TMA, 5 generic one-thread-per-output kernel, 6 8x16-tile kernel (channels split two ways).
- * Variants 1-4 and 6 need kernel_size=1, stride1=stride2=1, max_displacement>=4 (else CERB_EUNSUPPORTED). */
+ * without TMA, 5 generic one-thread-per-output kernel, 6 8x16-tile kernel (channels split two ways),
+ * 7 tensor-core kernel (tcgen05 / TMEM; fp32 via a 3xTF32 split, max_displacement 4 only: what auto picks from 64 tiles of 8x16).
+ * Variants 1-4 and 6 need kernel_size=1, stride1=stride2=1, max_displacement>=4, variant 7 additionally fp32 and
+ * max_displacement == 4 (else CERB_EUNSUPPORTED / cudaErrorNotSupported). */
 CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const void* x1, const void* x2,
                                             const float* flow, void* out, int variant, cerb_stream_t stream);
 

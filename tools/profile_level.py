@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Run one pyramid level a few times for ncu.
+"""Run one pyramid level a few times for ncu (both flow directions per launch, as the bench does).
     python tools/profile_level.py LEVEL VARIANT ITERS [rotate=1] [flow=1]"""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
@@ -17,10 +17,10 @@ C, H, W, wp = bench.PWC_LEVELS[li]
 dev = torch.device("cuda:0")
 sets = []
 for s in range(10 if rotate else 1):
-    x1, x2, fl = bench.synth_level(li, C, H, W, True, 1000 + 100 * s, dev)
-    sets.append((x1, x2, fl if use_flow else None, torch.empty(1, 81, H, W, device=dev)))
+    f, fl = bench.synth_level(li, C, H, W, True, 1000 + 100 * s, dev)
+    sets.append((f, fl if use_flow else None, torch.empty(bench.DIRS, 81, H, W, device=dev)))
 for i in range(iters):
-    x1, x2, fl, out = sets[i % len(sets)]
-    ops.warp_corr_forward(x1, x2, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out, variant=variant)
+    f, fl, out = sets[i % len(sets)]
+    ops.warp_corr_forward(f, f, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=out, variant=variant, x2_roll=bench.DIRS // 2)
 torch.cuda.synchronize()
 print("done")

@@ -41,6 +41,22 @@ for dt in (torch.float32, torch.float16):
     ops.warp_corr_forward(a, a, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=1)
     ops.warp_corr_forward(a, a, None, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=1)
 torch.cuda.synchronize()
+# tensor-core forward (variant 7): persistent loop over several tiles, 48 K steps, ragged / unaligned, pad != md, direct gather,
+# no flow, fused up-sampling; and the fused backward at a shape with several tiles per image
+a = torch.randn(3, 16, 64, 160, device=dev); fl = torch.randn(3, 2, 64, 160, device=dev) * 2
+ops.warp_corr_forward(a, a, fl, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=7, x2_roll=1)   # 120 tiles > CTAs on small parts only
+ops.warp_corr_forward(torch.randn(6, 8, 128, 256, device=dev), torch.randn(6, 8, 128, 256, device=dev),
+                      torch.randn(6, 2, 128, 256, device=dev), 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=7)   # 768 tiles: 5-6 per CTA
+run(1, 384, 16, 32, True, variant=7)
+run(2, 13, 21, 45, True, variant=7)
+run(1, 24, 30, 52, True, variant=7, pad=2)
+run(1, 24, 30, 52, True, variant=7, pad=6)
+run(1, 16, 32, 64, True, variant=7, sigma=20.0)
+run(2, 32, 24, 64, False, variant=7)
+a = torch.randn(2, 16, 64, 128, device=dev); coarse = torch.randn(2, 2, 32, 64, device=dev)
+cat = torch.zeros(2, 83, 64, 128, device=dev)
+ops.warp_corr_forward_upflow(a, a, coarse, 4, 1, 4, 1, 1, 1, cb.WARP_TORCH, 0.1, out=cat[:, :-2], flow_up=cat[:, -2:])   # 64 tiles -> tensor-core path
+torch.cuda.synchronize()
 x = torch.randn(1, 6, 12, 20, device=dev); f = torch.randn(1, 2, 12, 20, device=dev) * 3
 o = ops.flow_warp_forward(x, f); ops.flow_warp_backward(x, f, torch.randn_like(o))
 ops.warp_corr_forward(x, x, f, 3, 3, 4, 2, 2); torch.cuda.synchronize()
