@@ -640,8 +640,12 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           for (int ks = 0; ks < nks; ++ks, ++rc) {
             const int rs = rc % RS, ruse = rc / RS;
             tc_wait(&raw_empty[rs], (uint32_t)((ruse & 1) ^ 1));
+#ifdef CERB_TCX_NOTMA   // timing experiment only: the stage "lands" at once (stale data)
+            mbar_arrive(&raw_full[rs]);
+#else
             mbar_arrive_expect_tx(&raw_full[rs], RAW_STAGE);
             tma_load_4d(smem + OFF_RAW + (uint32_t)rs * RAW_STAGE, &tm_raw, &raw_full[rs], ox, oy, ks * KC, x2_item(g, n));
+#endif
             if (ks < 4) TC_TRACE(ti, 16 + ks);
           }
         }
