@@ -107,7 +107,13 @@ struct Args {
   long long* dbg;       // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer), 192 slots per CTA
 };
 // trace slot `s` of tile iteration `ti` (first four tiles of a CTA; 40 slots each)
+// (compiled in only with -DCERB_TC_TRACE: `python tools/ab_variants.py trace:-DCERB_TC_TRACE`; each point costs ~15 instructions
+// even when off at run time, and the gather and drain loops are bound by instruction issue)
+#ifdef CERB_TC_TRACE
 #define TC_TRACE(ti, s) do { if (a.dbg && (ti) < 4) a.dbg[(long long)blockIdx.x * 192 + 1 + (ti) * 40 + (s)] = clock64(); } while (0)
+#else
+#define TC_TRACE(ti, s) do { } while (0)
+#endif
 
 // ---- tcgen05 wrappers
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, 8-row atoms 1024 bytes apart
@@ -169,11 +175,11 @@ __device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
-// hi = tf32(v) (round to nearest, low 13 mantissa bits zero), lo = v - hi (exact)
+// hi = tf32(v): round to nearest (ties away) by adding half an ulp of the 10-bit mantissa to the bit pattern and clearing the
+// low 13 bits -- what cvt.rna.tf32.f32 computes for finite values, in 2 instructions instead of the 4 (with an Inf / NaN
+// guard) that cvt is expanded to; lo = v - hi (exact).  Non-finite inputs give non-finite outputs either way.
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(v));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
   lo = v - hi;
 }
 
@@ -228,7 +234,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+#ifdef CERB_TC_TRACE
   if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 192] = clock64();
+#endif
   // PDL: everything above overlapped the previous kernel's tail; its outputs may be our inputs
   pdl_wait();
 
@@ -245,6 +253,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     const int py = pl >> 4, px = pl & 15;
     const float fC = (float)g.C, rC = __frcp_rn((float)g.C);
     const bool c_pow2 = (g.C & (g.C - 1)) == 0;   // 1/C exact: the division is one multiply
+    const float act_slope = g.has_act ? g.slope : 1.f;   // no activation = slope 1
     const long long os1 = g.os[1];
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     // x1: 32 channels of this thread's pixel are requested in one burst and consumed right away (loads interleaved with
@@ -316,11 +325,20 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         if (pix_ok && dy >= 0 && dy <= 2 * MD) {
           T* orow = op + (long long)(dy * (2 * MD + 1)) * os1;
 #pragma unroll
-          for (int dx = 0; dx < 2 * MD + 1; ++dx) {
-            float r = c_pow2 ? __fmul_rn(__uint_as_float(v[dx]), rC) : div_const(__uint_as_float(v[dx]), fC, rC);
-            if (g.has_act) r = leaky(r, g.slope);
-            *orow = from_f32<T>(r);
-            orow += os1;
+          if (c_pow2) {
+#pragma unroll
+            for (int dx = 0; dx < 2 * MD + 1; ++dx) {
+              const float r = __fmul_rn(__uint_as_float(v[dx]), rC);
+              *orow = from_f32<T>(r > 0.f ? r : r * act_slope);
+              orow += os1;
+            }
+          } else {
+#pragma unroll
+            for (int dx = 0; dx < 2 * MD + 1; ++dx) {
+              const float r = div_const(__uint_as_float(v[dx]), fC, rC);
+              *orow = from_f32<T>(r > 0.f ? r : r * act_slope);
+              orow += os1;
+            }
           }
         }
       };
@@ -513,7 +531,10 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         auto blend_half = [&](const float (&v)[4][4], float4& hi, float4& lo) {
           float h[4], l[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) split_tf32(valid ? blend(v[c][0], v[c][1], v[c][2], v[c][3], tp) : 0.f, h[c], l[c]);
+          for (int c = 0; c < 4; ++c) {   // unconditional blend, validity as a select (a branch here diverges per lane)
+            const float r = blend(v[c][0], v[c][1], v[c][2], v[c][3], tp);
+            split_tf32(valid ? r : 0.f, h[c], l[c]);
+          }
           hi = make_float4(h[0], h[1], h[2], h[3]);
           lo = make_float4(l[0], l[1], l[2], l[3]);
         };
@@ -572,8 +593,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           float hi[KC], lo[KC];
 #pragma unroll
           for (int c = 0; c < KC; ++c) {
-            const float r = (valid && ks * KC + c < g.C) ? blend(tv[c][0], tv[c][1], tv[c][2], tv[c][3], tp) : 0.f;
-            split_tf32(r, hi[c], lo[c]);
+            const float r = blend(tv[c][0], tv[c][1], tv[c][2], tv[c][3], tp);
+            split_tf32((valid && ks * KC + c < g.C) ? r : 0.f, hi[c], lo[c]);
           }
           stage_b(hi, lo, ks);
           fence_proxy_async_smem();
@@ -656,7 +677,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+#ifdef CERB_TC_TRACE
   if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 192 + 191] = clock64();
+#endif
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
