@@ -53,19 +53,15 @@ unsigned long long* get_path_counters();
 namespace tc {
 
 constexpr int TY = 8, TX = 16, M = TY * TX;           // output tile, MMA M
-constexpr int MD = 4;
-constexpr int HY = TY + 2 * MD, HX = TX + 2 * MD;     // 16 x 24 halo of the second map
-constexpr int N = HY * HX, NH = N / 2;                // 384 accumulator columns, two MMAs of N = 192
+constexpr int N = 384, NH = N / 2;                    // accumulator columns of one pass, two MMAs of N = 192
 #ifndef CERB_TC_MARGIN
 #define CERB_TC_MARGIN 6
 #endif
 constexpr int MARGIN = CERB_TC_MARGIN;                // flow variation (px) inside one halo the raw box absorbs
-constexpr int RAW_H = HY + 2 * MARGIN + 2;            // 30
-constexpr int RAW_W = (HX + 2 * MARGIN + 2 + 3 + 3) / 4 * 4;   // 44 (box starts are 16-byte aligned)
 constexpr int KC = 8;                                 // channels per K step (32 bytes of a K-major row = one tf32 MMA)
 constexpr int SLOTS = 4;                              // K steps per 128-byte operand row
 constexpr int RS = 3;                                 // raw boxes in flight
-constexpr int EPI_WARPS = 8, GATHER_WARPS = 12, A_WARPS = 4;   // drain / gather / (of the gather warps) x1 conversion
+constexpr int EPI_WARPS = 8, GATHER_WARPS = 12, A_WARPS = 4;   // drain / gather / (of the drain warps) x1 staging
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, TMA_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = (TMA_WARP + 1) * 32;         // 704
@@ -73,16 +69,30 @@ constexpr uint32_t B_BYTES = N * 128;
 constexpr uint32_t OFF_BHI = 0, OFF_BLO = B_BYTES;
 constexpr uint32_t OFF_RAW = 2 * B_BYTES;
 constexpr uint32_t TMEM_A = N;                        // x1 operand: TMEM columns 384 + 16 slot (8 hi, 8 lo)
-constexpr uint32_t RAW_PLANE = RAW_H * RAW_W * 4;
-constexpr uint32_t RAW_STAGE = KC * RAW_PLANE;        // raw x2 box of a K step
-constexpr uint32_t OFF_RED = OFF_RAW + RS * RAW_STAGE;
-constexpr uint32_t OFF_BAR = OFF_RED + 2 * GATHER_WARPS * 4 * 4;
 constexpr int NBARS = 3 * SLOTS + 2 * RS + 2 + 4;
-constexpr uint32_t OFF_TMEM = OFF_BAR + NBARS * 8;
-constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
-static_assert(RAW_STAGE % 128 == 0 && OFF_RAW % 1024 == 0, "TMA destination alignment");
-static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(N == GATHER_THREADS && M == A_WARPS * 32 && EPI_WARPS == 8, "one halo position / one pixel per thread");
+
+// Geometry per max_displacement.  md 4: the 16 x 24 halo of an 8 x 16 tile is one accumulator pass (N = 384).  md 8: the
+// halo is 24 x 32 = 768 positions -- two passes of 12 x 32 (N = 384 each): a work unit is (tile, pass), pixel row py finds
+// its displacement rows py..py+16 in pass 0 (halo rows 0-11) and pass 1 (rows 12-23).
+template <int MD_>
+struct Geo {
+  static constexpr int MD = MD_, D = 2 * MD_ + 1;
+  static constexpr int NPASS = MD_ == 4 ? 1 : 2;
+  static constexpr int HYB = (TY + 2 * MD_) / NPASS;          // halo rows per pass: 16 / 12
+  static constexpr int HX = TX + 2 * MD_;                     // halo columns: 24 / 32
+  static constexpr int RAW_H = HYB + 2 * MARGIN + 2;          // 30 / 26
+  static constexpr int RAW_W = (HX + 2 * MARGIN + 2 + 3 + 3) / 4 * 4;   // 44 / 52 (box starts are 16-byte aligned)
+  static constexpr uint32_t RAW_PLANE = RAW_H * RAW_W * 4;
+  static constexpr uint32_t RAW_STAGE = KC * RAW_PLANE;       // raw x2 box of a K step
+  static constexpr uint32_t OFF_RED = OFF_RAW + RS * RAW_STAGE;
+  static constexpr uint32_t OFF_BAR = OFF_RED + 2 * GATHER_WARPS * 4 * 4;
+  static constexpr uint32_t OFF_TMEM = OFF_BAR + NBARS * 8;
+  static constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
+  static_assert(HYB * HX == N && (TY + 2 * MD_) % NPASS == 0 && HX == D + 15, "halo pass = 384 positions; shift network");
+  static_assert(RAW_STAGE % 128 == 0 && OFF_RAW % 1024 == 0, "TMA destination alignment");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
 
 enum { PATH_RAW = 1, PATH_DIRECT = 2 };   // indices match costvolume_fwd.cu's path counters
 
@@ -93,7 +103,7 @@ struct Args {
   const float* flow;
   void* out;
   int off;              // md - pad
-  int tiles_x, tiles_y, total_tiles;
+  int tiles_x, tiles_y, total_tiles;   // total_tiles counts work units: (tile, accumulator pass)
   int nks;              // K steps per tile: ceil(C / 8)
   int use_raw;          // raw x2 boxes by TMA
   // fused flow up-sampling (cerb_warp_corr_forward_upflow): coarse flow in, up-sampled flow out (cflow == nullptr: off)
@@ -160,6 +170,9 @@ __device__ __forceinline__ void tmem_ld_wait24(uint32_t* v) {
   asm volatile("" : "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) : : "memory");
   asm volatile("" : "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]) : : "memory");
 }
+__device__ __forceinline__ void tmem_ld_tie8(uint32_t* v) {   // (extends tmem_ld_wait24 to a fourth group of eight registers)
+  asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) : : "memory");
+}
 __device__ __forceinline__ int slot_of(int kc) { return kc & 3; }
 // Every wait carries a suspend-time hint: the waiting warp sleeps in hardware until the phase completes instead of
 // re-polling.  mbarrier polls are shared-memory operations; with 22 warps of which most are waiting at any time, plain
@@ -183,9 +196,13 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   lo = v - hi;
 }
 
-template <typename T>
+template <typename T, int MDT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw) {
+  using G = Geo<MDT>;
+  constexpr int MD = G::MD, D = G::D, NPASS = G::NPASS, HYB = G::HYB, HX = G::HX, RAW_H = G::RAW_H, RAW_W = G::RAW_W;
+  constexpr uint32_t RAW_PLANE = G::RAW_PLANE, RAW_STAGE = G::RAW_STAGE, OFF_RED = G::OFF_RED, OFF_BAR = G::OFF_BAR,
+                     OFF_TMEM = G::OFF_TMEM;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
@@ -242,6 +259,15 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 
   const int per_img = a.tiles_x * a.tiles_y;
   const int nks = a.nks;
+  // work unit -> batch item, tile origin (output coordinates), accumulator pass
+  auto decode = [&](int unit, int& n, int& by0, int& bx0, int& pass) {
+    pass = NPASS > 1 ? unit % NPASS : 0;
+    const int t = NPASS > 1 ? unit / NPASS : unit;
+    n = t / per_img;
+    const int trem = t - n * per_img;
+    by0 = (trem / a.tiles_x) * TY;
+    bx0 = (trem % a.tiles_x) * TX;
+  };
 
   if (warp < EPI_WARPS) {
     // =========================== x1 operand (warps 4-7) + accumulator drain: thread = pixel ===========================
@@ -260,8 +286,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     // the consumption of older ones made every use wait for the youngest: scoreboards count, they do not track loads)
     int ka = 0;   // K steps staged so far (all tiles)
     auto stage_a_group = [&](int tile, int ks0) {
-      const int n = tile / per_img, trem = tile - n * per_img;
-      const int iy = (trem / a.tiles_x) * TY + a.off + py, ix = (trem % a.tiles_x) * TX + a.off + px;
+      int n, by0, bx0, pass;
+      decode(tile, n, by0, bx0, pass);
+      const int iy = by0 + a.off + py, ix = bx0 + a.off + px;
       const bool inimg = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const T* p = x1 + (long long)n * g.x1s[0] + (long long)min(max(iy, 0), g.H - 1) * g.x1s[2] + min(max(ix, 0), g.W - 1);
       float nx[SLOTS][KC];
@@ -302,66 +329,90 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         if (tile + (int)gridDim.x < a.total_tiles) stage_a_group(tile + gridDim.x, 0);
         if (warp == A_WARPS && lane == 0) TC_TRACE(ti, 26);
       }
-      const int n = tile / per_img, trem = tile - n * per_img;
-      const int oy = (trem / a.tiles_x) * TY + py, ox = (trem % a.tiles_x) * TX + px;
+      int n, by0, bx0, pass;
+      decode(tile, n, by0, bx0, pass);
+      const int oy = by0 + py, ox = bx0 + px;
       const bool pix_ok = oy < g.outH && ox < g.outW;
       T* op = (T*)a.out + (long long)n * g.os[0] + (long long)min(oy, g.outH - 1) * g.os[2] + min(ox, g.outW - 1);
       tc_wait(d_full, (uint32_t)(ti & 1));
       tc_fence_after();
       if (tid == 0) TC_TRACE(ti, 30);
-      const int rr0 = a_warp ? 6 : 0, rr1 = a_warp ? 10 : 6;
-      // two halo rows per iteration: their select networks and stores are independent instruction streams (one warp
-      // per sub-partition drains at a time -- what it lacks is instruction-level parallelism, not issue slots)
-      auto finish_row = [&](uint32_t (&v)[24], int rr) {
+      // halo rows (of the whole halo) this pass holds that the quadrant's pixel rows 2q, 2q+1 need; the two warps of a
+      // quadrant split them (the x1-staging warp takes the smaller share)
+      const int r_lo = max(pass * HYB, 2 * q), r_hi = min(pass * HYB + HYB, 2 * q + 1 + D);   // [r_lo, r_hi), an even count
+      const int n0 = 2 * (((r_hi - r_lo) / 2 + 1) / 2);
+      const int rr0 = a_warp ? r_lo + n0 : r_lo, rr1 = a_warp ? r_hi : r_lo + n0;
+      // one halo row of the accumulator: shift by the lane's own x (select network: the column offset differs per lane,
+      // tcgen05.ld's does not), divide, activate, store the D displacement columns of displacement row r - py
+      auto finish_row = [&](uint32_t* v, int r) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = (px & 8) ? v[i + 8] : v[i];
+        for (int i = 0; i < D + 7; ++i) v[i] = (px & 8) ? v[i + 8] : v[i];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) v[i] = (px & 4) ? v[i + 4] : v[i];
+        for (int i = 0; i < D + 3; ++i) v[i] = (px & 4) ? v[i + 4] : v[i];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) v[i] = (px & 2) ? v[i + 2] : v[i];
+        for (int i = 0; i < D + 1; ++i) v[i] = (px & 2) ? v[i + 2] : v[i];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) v[i] = (px & 1) ? v[i + 1] : v[i];
-        const int dy = rr - (py & 1);   // halo row 2q + rr is displacement row (2q + rr) - py of this pixel
-        if (pix_ok && dy >= 0 && dy <= 2 * MD) {
-          T* orow = op + (long long)(dy * (2 * MD + 1)) * os1;
-#pragma unroll
+        for (int i = 0; i < D; ++i) v[i] = (px & 1) ? v[i + 1] : v[i];
+        const int dy = r - py;
+        if (pix_ok && dy >= 0 && dy < D) {
+          T* orow = op + (long long)(dy * D) * os1;
           if (c_pow2) {
 #pragma unroll
-            for (int dx = 0; dx < 2 * MD + 1; ++dx) {
-              const float r = __fmul_rn(__uint_as_float(v[dx]), rC);
-              *orow = from_f32<T>(r > 0.f ? r : r * act_slope);
+            for (int dx = 0; dx < D; ++dx) {
+              const float res = __fmul_rn(__uint_as_float(v[dx]), rC);
+              *orow = from_f32<T>(res > 0.f ? res : res * act_slope);
               orow += os1;
             }
           } else {
 #pragma unroll
-            for (int dx = 0; dx < 2 * MD + 1; ++dx) {
-              const float r = div_const(__uint_as_float(v[dx]), fC, rC);
-              *orow = from_f32<T>(r > 0.f ? r : r * act_slope);
+            for (int dx = 0; dx < D; ++dx) {
+              const float res = div_const(__uint_as_float(v[dx]), fC, rC);
+              *orow = from_f32<T>(res > 0.f ? res : res * act_slope);
               orow += os1;
             }
           }
         }
       };
+      auto release = [&]() {   // every load of this warp has landed: (with the other seven) the next unit's MMAs may start
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_empty);
+        if (tid == 0) TC_TRACE(ti, 31);
+      };
+      if (rr0 >= rr1) release();
+      if constexpr (MDT == 4) {
+        // two halo rows per iteration: their select networks and stores are independent instruction streams (one warp
+        // per sub-partition drains at a time -- what it lacks is instruction-level parallelism, not issue slots)
 #pragma unroll 1
-      for (int rr = rr0; rr < rr1; rr += 2) {
-        uint32_t v0[24], v1[24];
-        const uint32_t col = (uint32_t)((2 * q + rr) * HX);
-        tmem_ld8(tlane + col, v0);
-        tmem_ld8(tlane + col + 8, v0 + 8);
-        tmem_ld8(tlane + col + 16, v0 + 16);
-        tmem_ld8(tlane + col + HX, v1);
-        tmem_ld8(tlane + col + HX + 8, v1 + 8);
-        tmem_ld8(tlane + col + HX + 16, v1 + 16);
-        tmem_ld_wait24(v0);
-        tmem_ld_wait24(v1);
-        if (rr == rr1 - 2) {   // every load of this warp has landed: (with the other seven) the next tile's MMAs may start
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d_empty);
-          if (tid == 0) TC_TRACE(ti, 31);
+        for (int r = rr0; r < rr1; r += 2) {
+          uint32_t v0[24], v1[24];
+          const uint32_t col = (uint32_t)((r - pass * HYB) * HX);
+          tmem_ld8(tlane + col, v0);
+          tmem_ld8(tlane + col + 8, v0 + 8);
+          tmem_ld8(tlane + col + 16, v0 + 16);
+          tmem_ld8(tlane + col + HX, v1);
+          tmem_ld8(tlane + col + HX + 8, v1 + 8);
+          tmem_ld8(tlane + col + HX + 16, v1 + 16);
+          tmem_ld_wait24(v0);
+          tmem_ld_wait24(v1);
+          if (r == rr1 - 2) release();
+          finish_row(v0, r);
+          finish_row(v1, r + 1);
         }
-        finish_row(v0, rr);
-        finish_row(v1, rr + 1);
+      } else {
+#pragma unroll 1
+        for (int r = rr0; r < rr1; ++r) {
+          uint32_t v[32];
+          const uint32_t col = (uint32_t)((r - pass * HYB) * HX);
+          tmem_ld8(tlane + col, v);
+          tmem_ld8(tlane + col + 8, v + 8);
+          tmem_ld8(tlane + col + 16, v + 16);
+          tmem_ld8(tlane + col + 24, v + 24);
+          tmem_ld_wait24(v);
+          tmem_ld_tie8(v + 24);
+          if (r == rr1 - 1) release();
+          finish_row(v, r);
+        }
       }
       if (tid == 0) TC_TRACE(ti, 32);
     }
@@ -380,16 +431,17 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       bool valid;
     };
     // halo position of a tile -> clamped pixel (the flow vector is read there), inside-the-image flag
-    auto locate = [&](int tile, int& n, int& cy, int& cx) -> bool {
-      n = tile / per_img;
-      const int trem = tile - n * per_img;
-      const int qy = (trem / a.tiles_x) * TY + a.off - g.md + hy, qx = (trem % a.tiles_x) * TX + a.off - g.md + hx;
+    auto locate = [&](int tile, int& n, int& cy, int& cx, int& ghy) -> bool {
+      int by0, bx0, pass;
+      decode(tile, n, by0, bx0, pass);
+      ghy = pass * HYB + hy;   // row inside the tile's whole halo
+      const int qy = by0 + a.off - MD + ghy, qx = bx0 + a.off - MD + hx;
       cy = min(max(qy, 0), g.H - 1); cx = min(max(qx, 0), g.W - 1);
       return qy >= 0 && qy < g.H && qx >= 0 && qx < g.W;   // outside: the correlation's zero padding
     };
     auto load_flow = [&](int tile, float& fu, float& fv) {
-      int n, cy, cx;
-      const bool inside = locate(tile, n, cy, cx);
+      int n, cy, cx, ghy;
+      const bool inside = locate(tile, n, cy, cx, ghy);
       if (!upflow) {
         const float* fp = a.flow + (long long)n * g.fls[0] + (long long)cy * g.fls[2] + cx;
         fu = __ldg(fp); fv = __ldg(fp + g.fls[1]);
@@ -423,7 +475,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       }
       fu = r[0]; fv = r[1];
       // positions inside the tile itself (each pixel of the image exactly once) also write the up-sampled flow out
-      if (inside && hy >= g.md && hy < g.md + TY && hx >= g.md && hx < g.md + TX) {
+      if (inside && ghy >= MD && ghy < MD + TY && hx >= MD && hx < MD + TX) {
         float* up = a.flow_up + (long long)n * a.fus[0] + (long long)cy * a.fus[2] + cx;
         up[0] = r[0];
         up[a.fus[1]] = r[1];
@@ -431,9 +483,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     };
     // taps of the tile and this warp's share of their bounding box (published for tile iteration `it`)
     auto prepare = [&](int tile, int it, float fu, float fv) -> Pos {
-      int n, cy, cx;
+      int n, cy, cx, ghy;
       Pos p;
-      p.valid = locate(tile, n, cy, cx);
+      p.valid = locate(tile, n, cy, cx, ghy);
       float sx = (float)cx, sy = (float)cy;   // un-warped: the pixel itself (weights 1, 0, 0, 0)
       if (warped) {
         bool in_x, in_y;
@@ -472,7 +524,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     nxt = cur;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
       if (gt == 0) TC_TRACE(ti, 0);
-      const int n = tile / per_img;
+      int n, by0_, bx0_, pass_;
+      decode(tile, n, by0_, bx0_, pass_);
       const bool has_next = tile + (int)gridDim.x < a.total_tiles;
       float nfu = 0.f, nfv = 0.f;   // the next tile's flow vector: requested now, used after the first K step
       if (has_next && warped) load_flow(tile + gridDim.x, nfu, nfv);
@@ -644,7 +697,8 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     if (a.use_raw && lane == 0) {
       int rc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        const int n = tile / per_img;
+        int n, by0_, bx0_, pass_;
+        decode(tile, n, by0_, bx0_, pass_);
         tc_wait(&bbox_full[ti & 1], (uint32_t)((ti >> 1) & 1));
         TC_TRACE(ti, 15);
         const int4* rp = reinterpret_cast<const int4*>(red + (ti & 1) * (GATHER_WARPS * 4));
@@ -690,19 +744,20 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 
 bool tc_forward_supported(const Geom& g, int dtype, const UpFlow* uf) {
   if (uf != nullptr && (g.pad != g.md || (g.H & 1) || (g.W & 1))) return false;   // tiles must cover the image exactly once
-  return dtype == CERB_F32 && g.k == 1 && g.s1 == 1 && g.s2 == 1 && g.md == tc::MD && g.outH > 0 && g.outW > 0;
+  return dtype == CERB_F32 && g.k == 1 && g.s1 == 1 && g.s2 == 1 && (g.md == 4 || g.md == 8) && g.outH > 0 && g.outW > 0;
 }
 
-cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
-                                        cudaStream_t stream, const UpFlow* uf) {
-  if (!tc_forward_supported(g, dtype, uf)) return cudaErrorNotSupported;
+template <int MDT>
+static cudaError_t launch_tc_md(const Geom& g, const void* x1, const void* x2, const float* flow, void* out, cudaStream_t stream,
+                                const UpFlow* uf) {
+  using G = tc::Geo<MDT>;
   tc::Args a;
   a.g = g;
   a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out;
   a.off = g.md - g.pad;
   a.tiles_x = (g.outW + tc::TX - 1) / tc::TX;
   a.tiles_y = (g.outH + tc::TY - 1) / tc::TY;
-  a.total_tiles = g.B * a.tiles_x * a.tiles_y;
+  a.total_tiles = g.B * a.tiles_x * a.tiles_y * G::NPASS;
   a.nks = (g.C + tc::KC - 1) / tc::KC;
   a.path_ctr = get_path_counters();
   a.dbg = get_trace_buffer();
@@ -719,16 +774,16 @@ cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1
   memset(&tm_raw, 0, sizeof(tm_raw));
   a.use_raw = 0;
   if (!getenv("CERB_DEBUG_TC_NO_RAW"))   // TMA needs 16-byte aligned base / strides (make_tmap_nchw checks)
-    a.use_raw = make_tmap_nchw(&tm_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, tc::RAW_W, tc::RAW_H,
+    a.use_raw = make_tmap_nchw(&tm_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, G::RAW_W, G::RAW_H,
                                tc::KC, false) ? 1 : 0;
-  auto kern = tc::warp_corr_fwd_tc_kernel<float>;
+  auto kern = tc::warp_corr_fwd_tc_kernel<float, MDT>;
   static unsigned long long attr_devs = 0ull;   // function attributes are per device
   {
     int dev = 0;
     cudaGetDevice(&dev);
     const unsigned long long bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
     if (bit == 0ull || !(attr_devs & bit)) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES);
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_BYTES);
       if (e != cudaSuccess) return e;
       attr_devs |= bit;
     }
@@ -738,7 +793,7 @@ cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(tc::NTHREADS);
-  cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   int na = 0;
@@ -753,6 +808,12 @@ cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1
   cudaError_t le = cudaLaunchKernelEx(&cfg, kern, a, tm_raw);
   if (le != cudaSuccess) return le;
   return cudaGetLastError();
+}
+
+cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
+                                        cudaStream_t stream, const UpFlow* uf) {
+  if (!tc_forward_supported(g, dtype, uf)) return cudaErrorNotSupported;
+  return g.md == 4 ? launch_tc_md<4>(g, x1, x2, flow, out, stream, uf) : launch_tc_md<8>(g, x1, x2, flow, out, stream, uf);
 }
 
 }  // namespace cerb

@@ -57,6 +57,24 @@ def test_tc_forward_vs_oracle(B, C, H, W, pad, sigma, mode):
     assert bool((buf[:, ref.shape[1]:] == 7.0).all())
 
 
+@pytest.mark.parametrize("B,C,H,W,pad,sigma", [
+    (2, 32, 48, 160, 8, 1.5),     # KITTI-shaped level (BASELINE configs[4]): 60 tiles x 2 accumulator passes per image
+    (1, 20, 19, 37, 8, 2.5),      # ragged, no TMA
+    (1, 8, 32, 48, 6, 1.5),       # pad < md
+    (2, 40, 16, 32, 8, None),     # no flow, C % 8 != 0 handled by zero-filled K step
+    (1, 16, 24, 64, 8, 15.0),     # direct gather
+])
+def test_tc_forward_md8_vs_oracle(B, C, H, W, pad, sigma):
+    """max_displacement 8 (289 planes): the 24 x 32 halo is two accumulator passes of 12 x 32 positions."""
+    x1, x2, fl = case(B * 100 + C, B, C, H, W, sigma)
+    ref = co.level_forward(x1, x2, fl, pad, 1, 8, 1, 1, co.WARP_TORCH, 0.1)
+    t1, t2 = torch.from_numpy(x1).to(dev()), torch.from_numpy(x2).to(dev())
+    tf = torch.from_numpy(fl).to(dev()) if fl is not None else None
+    out = ops.warp_corr_forward(t1, t2, tf, pad, 1, 8, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=TC)
+    assert out.shape[1] == 289
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+
+
 def test_tc_forward_no_activation_and_roll():
     x1, _, fl = case(5, 4, 40, 32, 80, 2.0)
     f = torch.from_numpy(x1).to(dev())
