@@ -34,6 +34,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <type_traits>
 
 #include "costvolume_common.cuh"
@@ -1321,6 +1322,37 @@ static bool make_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const 
                       const long long strides[3], int bx, int by, int bc, bool swizzle128) {
   return make_tmap_nchw(tm, dt, esize, base, W, H, C, B, strides, bx, by, bc, swizzle128);
 }
+// Encoded tensor maps are cached: a decoder calls the op with the same buffers every step, and one encode costs about a
+// microsecond of host time (up to six per launch).  Key = everything the encode depends on; a small direct-mapped table
+// under a mutex (the C ABI may be called from several host threads); a map is a pure function of its key, so a stale
+// entry for a freed-and-reallocated pointer with the same geometry is still the right map.
+struct TmapKey {
+  unsigned long long base;
+  long long s0, s1, s2;
+  int dt, esize, W, H, C, B, bx, by, bc, kind;   // kind: 0/1 = NCHW map without / with swizzle, 2 = 5-D output map (bc = D)
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool used; };
+static TmapSlot g_tmap_cache[256];
+static std::mutex g_tmap_mutex;
+static unsigned tmap_hash(const TmapKey& k) {
+  unsigned long long h = k.base * 0x9E3779B97F4A7C15ull;
+  h ^= (unsigned long long)(k.bx * 131 + k.by * 31 + k.bc * 7 + k.kind * 3 + k.dt) * 0xC2B2AE3D27D4EB4Full;
+  h ^= (unsigned long long)k.s0 * 0x165667B19E3779F9ull;
+  return (unsigned)(h >> 40) & 255u;
+}
+static bool tmap_lookup(const TmapKey& k, CUtensorMap* tm) {
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  const TmapSlot& s = g_tmap_cache[tmap_hash(k)];
+  if (!s.used || memcmp(&s.key, &k, sizeof(TmapKey)) != 0) return false;
+  *tm = s.map;
+  return true;
+}
+static void tmap_store(const TmapKey& k, const CUtensorMap& tm) {
+  std::lock_guard<std::mutex> lock(g_tmap_mutex);
+  TmapSlot& s = g_tmap_cache[tmap_hash(k)];
+  s.key = k; s.map = tm; s.used = true;
+}
+
 // (also used by costvolume_fwd_tc.cu)
 bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
                     const long long strides[3], int bx, int by, int bc, bool swizzle128) {
@@ -1330,6 +1362,12 @@ bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const vo
   for (int i = 0; i < 3; ++i)
     if (strides[i] <= 0 || (strides[i] * esize) % 16 != 0) return false;
   if (bx > 256 || by > 256 || bc > 256 || (bx * esize) % 16 != 0) return false;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = (unsigned long long)(uintptr_t)base; key.s0 = strides[0]; key.s1 = strides[1]; key.s2 = strides[2];
+  key.dt = (int)dt; key.esize = esize; key.W = W; key.H = H; key.C = C; key.B = B; key.bx = bx; key.by = by; key.bc = bc;
+  key.kind = swizzle128 ? 1 : 0;
+  if (tmap_lookup(key, tm)) return true;
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
   cuuint64_t gstr[3] = {(cuuint64_t)strides[2] * esize, (cuuint64_t)strides[1] * esize, (cuuint64_t)strides[0] * esize};
   cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bc, 1};
@@ -1337,6 +1375,7 @@ bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const vo
   CUresult r = enc(tm, dt, 4, const_cast<void*>(base), dims, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_store(key, *tm);
   return r == CUDA_SUCCESS;
 }
 static bool make_tmap_f32(CUtensorMap* tm, const void* base, int W, int H, int C, int B, const long long strides[3],
@@ -1351,6 +1390,12 @@ static bool make_tmap_out5d(CUtensorMap* tm, const void* base, const Geom& g, in
   if (((uintptr_t)base & 15) != 0) return false;
   for (int i = 0; i < 3; ++i)
     if (g.os[i] <= 0 || (g.os[i] * 4) % 16 != 0) return false;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = (unsigned long long)(uintptr_t)base; key.s0 = g.os[0]; key.s1 = g.os[1]; key.s2 = g.os[2];
+  key.dt = (int)CU_TENSOR_MAP_DATA_TYPE_FLOAT32; key.esize = 4; key.W = g.outW; key.H = g.outH; key.C = g.D; key.B = g.B;
+  key.bx = bx; key.by = by; key.bc = bdx; key.kind = 2;
+  if (tmap_lookup(key, tm)) return true;
   cuuint64_t dims[5] = {(cuuint64_t)g.outW, (cuuint64_t)g.outH, (cuuint64_t)g.D, (cuuint64_t)g.D, (cuuint64_t)g.B};
   cuuint64_t gstr[4] = {(cuuint64_t)g.os[2] * 4, (cuuint64_t)g.os[1] * 4, (cuuint64_t)g.os[1] * 4 * g.D, (cuuint64_t)g.os[0] * 4};
   cuuint32_t box[5] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bdx, (cuuint32_t)kD, 1};
@@ -1358,6 +1403,7 @@ static bool make_tmap_out5d(CUtensorMap* tm, const void* base, const Geom& g, in
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), dims, gstr, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, bx == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) tmap_store(key, *tm);
   return r == CUDA_SUCCESS;
 }
 

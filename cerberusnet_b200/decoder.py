@@ -7,8 +7,8 @@ detr_sfd.py:227-266): up-sample the flow x2 (values x2) -> warp the second featu
 context network.  Here the three hot-path ops are one launch (`warp_correlation`), and in eval
 mode the activated cost volume is written straight into the concat buffer.
 
-This module is a harness for measuring the path inside a training / inference step (bench.py
---workload train); the estimator and context stacks are plain torch convolutions, sized like the
+This module is a harness for measuring the path inside a training / inference step (the `train` block of
+bench.py, tools/train_bench.py); the estimator and context stacks are plain torch convolutions, sized like the
 reference's "lite" estimator, not a re-implementation of the reference models.
 """
 from __future__ import annotations
