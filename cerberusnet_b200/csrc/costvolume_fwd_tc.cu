@@ -58,38 +58,48 @@ constexpr int N = 384, NH = N / 2;                    // accumulator columns of 
 #define CERB_TC_MARGIN 6
 #endif
 constexpr int MARGIN = CERB_TC_MARGIN;                // flow variation (px) inside one halo the raw box absorbs
-constexpr int KC = 8;                                 // channels per K step (32 bytes of a K-major row = one tf32 MMA)
 constexpr int SLOTS = 4;                              // K steps per 128-byte operand row
-constexpr int RS = 3;                                 // raw boxes in flight
+constexpr int RS_MAX = 3;                             // raw boxes in flight (fp32: 3, 16-bit: 2)
 constexpr int EPI_WARPS = 8, GATHER_WARPS = 12, A_WARPS = 4;   // drain / gather / (of the drain warps) x1 staging
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, TMA_WARP = MMA_WARP + 1;
 constexpr int NTHREADS = (TMA_WARP + 1) * 32;         // 704
-constexpr uint32_t B_BYTES = N * 128;
-constexpr uint32_t OFF_BHI = 0, OFF_BLO = B_BYTES;
-constexpr uint32_t OFF_RAW = 2 * B_BYTES;
-constexpr uint32_t TMEM_A = N;                        // x1 operand: TMEM columns 384 + 16 slot (8 hi, 8 lo)
-constexpr int NBARS = 3 * SLOTS + 2 * RS + 2 + 4;
+constexpr uint32_t B_BYTES = N * 128, A_BYTES = M * 128;
+constexpr uint32_t OFF_BHI = 0;
+constexpr uint32_t TMEM_A = N;                        // fp32: x1 operand in TMEM columns 384 + 16 slot (8 hi, 8 lo)
+constexpr int NBARS = 3 * SLOTS + 2 * RS_MAX + 2 + 4;
 static_assert(N == GATHER_THREADS && M == A_WARPS * 32 && EPI_WARPS == 8, "one halo position / one pixel per thread");
 
 // Geometry per max_displacement.  md 4: the 16 x 24 halo of an 8 x 16 tile is one accumulator pass (N = 384).  md 8: the
 // halo is 24 x 32 = 768 positions -- two passes of 12 x 32 (N = 384 each): a work unit is (tile, pass), pixel row py finds
 // its displacement rows py..py+16 in pass 0 (halo rows 0-11) and pass 1 (rows 12-23).
-template <int MD_>
+// ES = element size of the inputs.  fp32 (ES 4): a K step is 8 channels (32 bytes of an operand row = one kind::tf32 MMA),
+// operands are hi / lo pairs (3xTF32), x1 lives in TMEM.  16-bit (ES 2): a K step is 16 channels (one kind::f16 MMA); x1 is
+// exact in T (a K-major shared-memory tile), the blended x2w is not, so it is kept as hi = T(v), lo = T(v - hi) and two
+// products accumulate (x1*hi + x1*lo): the result carries the one rounding of the stored output, as the CUDA-core path's does.
+template <int MD_, int ES>
 struct Geo {
   static constexpr int MD = MD_, D = 2 * MD_ + 1;
+  static constexpr bool F32 = ES == 4;
+  static constexpr int KC = 32 / ES;                          // channels per K step: 8 / 16
+  static constexpr int AL = 16 / ES;                          // elements per 16 bytes: TMA box starts are 16-byte aligned
   static constexpr int NPASS = MD_ == 4 ? 1 : 2;
   static constexpr int HYB = (TY + 2 * MD_) / NPASS;          // halo rows per pass: 16 / 12
   static constexpr int HX = TX + 2 * MD_;                     // halo columns: 24 / 32
   static constexpr int RAW_H = HYB + 2 * MARGIN + 2;          // 30 / 26
-  static constexpr int RAW_W = (HX + 2 * MARGIN + 2 + 3 + 3) / 4 * 4;   // 44 / 52 (box starts are 16-byte aligned)
-  static constexpr uint32_t RAW_PLANE = RAW_H * RAW_W * 4;
+  static constexpr int RAW_W = (HX + 2 * MARGIN + 2 + 2 * (AL - 1)) / AL * AL;   // fp32 44 / 52, 16-bit 48 / 56
+  static constexpr uint32_t RAW_PLANE = RAW_H * RAW_W * ES;
   static constexpr uint32_t RAW_STAGE = KC * RAW_PLANE;       // raw x2 box of a K step
+  static constexpr int RS = F32 ? 3 : 2;                      // raw boxes in flight
+  static constexpr uint32_t OFF_BLO = B_BYTES;                // lo tile of x2w
+  static constexpr uint32_t OFF_A = 2 * B_BYTES;              // 16-bit: the x1 tile
+  static constexpr uint32_t OFF_RAW = F32 ? 2 * B_BYTES : 2 * B_BYTES + A_BYTES;
   static constexpr uint32_t OFF_RED = OFF_RAW + RS * RAW_STAGE;
   static constexpr uint32_t OFF_BAR = OFF_RED + 2 * GATHER_WARPS * 4 * 4;
   static constexpr uint32_t OFF_TMEM = OFF_BAR + NBARS * 8;
   static constexpr uint32_t SMEM_BYTES = OFF_TMEM + 16 + 1024;
   static_assert(HYB * HX == N && (TY + 2 * MD_) % NPASS == 0 && HX == D + 15, "halo pass = 384 positions; shift network");
+  static_assert(RAW_W >= HX + 2 * MARGIN + 2 + AL - 1, "box covers the footprint after aligning its start down");
   static_assert(RAW_STAGE % 128 == 0 && OFF_RAW % 1024 == 0, "TMA destination alignment");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
@@ -160,6 +170,50 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// 16-bit operands (kind::f16: fp16 or bf16 per the instruction descriptor), both from shared memory
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);   // two values rounded to T, a in the low half
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<float>(float, float) { return 0u; }   // (never used)
+template <typename T> __device__ __forceinline__ float unpack_lo(uint32_t w);   // low / high half of a packed pair, widened
+template <typename T> __device__ __forceinline__ float unpack_hi(uint32_t w);
+template <> __device__ __forceinline__ float unpack_lo<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+template <> __device__ __forceinline__ float unpack_hi<__half>(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+template <> __device__ __forceinline__ float unpack_lo<__nv_bfloat16>(uint32_t w) { return __uint_as_float(w << 16); }
+template <> __device__ __forceinline__ float unpack_hi<__nv_bfloat16>(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+template <> __device__ __forceinline__ float unpack_lo<float>(uint32_t) { return 0.f; }
+template <> __device__ __forceinline__ float unpack_hi<float>(uint32_t) { return 0.f; }
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <typename T> __device__ __forceinline__ float lds_t(uint32_t addr);   // one input element from shared memory, widened
+template <> __device__ __forceinline__ float lds_t<float>(uint32_t addr) { return lds_f32(addr); }
+template <> __device__ __forceinline__ float lds_t<__half>(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return __half2float(__ushort_as_half(v));
+}
+template <> __device__ __forceinline__ float lds_t<__nv_bfloat16>(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return __uint_as_float((uint32_t)v << 16);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait for the loads into v[0..23]; the registers pass through the statement so that no use can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait24(uint32_t* v) {
@@ -199,10 +253,15 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 template <typename T, int MDT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw) {
-  using G = Geo<MDT>;
-  constexpr int MD = G::MD, D = G::D, NPASS = G::NPASS, HYB = G::HYB, HX = G::HX, RAW_H = G::RAW_H, RAW_W = G::RAW_W;
+  using G = Geo<MDT, (int)sizeof(T)>;
+  constexpr bool F32 = G::F32;
+  constexpr int MD = G::MD, D = G::D, NPASS = G::NPASS, HYB = G::HYB, HX = G::HX, RAW_H = G::RAW_H, RAW_W = G::RAW_W,
+                KC = G::KC, AL = G::AL, ES = (int)sizeof(T);
+  constexpr int RS = G::RS;
+  constexpr int NB = KC / 4;          // batches of 4 channels per K step (the gather's software-pipeline unit): 2 / 4
+  constexpr int AG = F32 ? SLOTS : 2; // K steps per x1 staging burst (32 channels: registers)
   constexpr uint32_t RAW_PLANE = G::RAW_PLANE, RAW_STAGE = G::RAW_STAGE, OFF_RED = G::OFF_RED, OFF_BAR = G::OFF_BAR,
-                     OFF_TMEM = G::OFF_TMEM;
+                     OFF_TMEM = G::OFF_TMEM, OFF_RAW = G::OFF_RAW, OFF_BLO = G::OFF_BLO, OFF_A = G::OFF_A;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
@@ -291,9 +350,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       const int iy = by0 + a.off + py, ix = bx0 + a.off + px;
       const bool inimg = iy >= 0 && iy < g.H && ix >= 0 && ix < g.W;
       const T* p = x1 + (long long)n * g.x1s[0] + (long long)min(max(iy, 0), g.H - 1) * g.x1s[2] + min(max(ix, 0), g.W - 1);
-      float nx[SLOTS][KC];
+      float nx[AG][KC];
 #pragma unroll
-      for (int b = 0; b < SLOTS; ++b)
+      for (int b = 0; b < AG; ++b)
 #pragma unroll
         for (int c = 0; c < KC; ++c) {   // unconditional loads from clamped addresses, validity applied afterwards
           const int ch = (ks0 + b) * KC + c;
@@ -301,18 +360,30 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           nx[b][c] = (inimg && ch < g.C) ? v : 0.f;
         }
 #pragma unroll
-      for (int b = 0; b < SLOTS; ++b) {
+      for (int b = 0; b < AG; ++b) {
         if (ks0 + b < nks) {
-          float hi[KC], lo[KC];
-#pragma unroll
-          for (int c = 0; c < KC; ++c) split_tf32(nx[b][c], hi[c], lo[c]);
           const int slot = ka & (SLOTS - 1), use = ka >> 2;
-          tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
-          tc_fence_after();
-          tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u, hi);
-          tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u + 8u, lo);
-          tmem_st_wait();
-          tc_fence_before();
+          if constexpr (F32) {
+            float hi[KC], lo[KC];
+#pragma unroll
+            for (int c = 0; c < KC; ++c) split_tf32(nx[b][c], hi[c], lo[c]);
+            tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+            tc_fence_after();
+            tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u, hi);
+            tmem_st8(tlane + TMEM_A + (uint32_t)slot * 16u + 8u, lo);
+            tmem_st_wait();
+            tc_fence_before();
+          } else {
+            // 16-bit: the pixel's row of the K-major x1 tile (the values are exact in T: they were loaded as T)
+            uint32_t w[KC / 2];
+#pragma unroll
+            for (int c = 0; c < KC / 2; ++c) w[c] = pack2<T>(nx[b][2 * c], nx[b][2 * c + 1]);
+            tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+            const uint32_t arow = sbase + OFF_A + (uint32_t)pl * 128u, sw = (uint32_t)(pl & 7);
+            sts128u(arow + ((((uint32_t)(2 * slot)) ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            sts128u(arow + ((((uint32_t)(2 * slot + 1)) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+            fence_proxy_async_smem();
+          }
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[slot]);
           ++ka;
@@ -325,7 +396,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       if (a_warp) {
         // the rest of this tile's x1 (slots free up as its MMAs retire), then the first group of the next tile: staged
         // while this tile's MMAs run, so the next tile's can start the moment the accumulator has drained
-        for (int ks0 = SLOTS; ks0 < nks; ks0 += SLOTS) stage_a_group(tile, ks0);
+        for (int ks0 = AG; ks0 < nks; ks0 += AG) stage_a_group(tile, ks0);
         if (tile + (int)gridDim.x < a.total_tiles) stage_a_group(tile + gridDim.x, 0);
         if (warp == A_WARPS && lane == 0) TC_TRACE(ti, 26);
       }
@@ -541,7 +612,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           xmin = min(xmin, b.x); xmax = max(xmax, b.y);
           ymin = min(ymin, b.z); ymax = max(ymax, b.w);
         }
-        ox = xmin & ~3;   // TMA box starts must be 16-byte aligned
+        ox = xmin & ~(AL - 1);   // TMA box starts must be 16-byte aligned
         oy = ymin;
         if (xmin <= xmax && xmax - ox < RAW_W && ymax - oy < RAW_H) path = PATH_RAW;
       }
@@ -551,73 +622,78 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       Taps tp;
 #pragma unroll
       for (int k = 0; k < 4; ++k) tp.w[k] = cur.w[k];
-      // the operand slot of this K step is free and written: publish it
-      auto stage_b = [&](const float (&hi)[KC], const float (&lo)[KC], int ks) {
-        const int slot = kc & (SLOTS - 1), use = kc >> 2;
-        tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
-        if (gt == 0 && ks < 4) TC_TRACE(ti, 4 + 3 * ks);
-        const uint32_t c0 = (((uint32_t)(2 * slot)) ^ sw) << 4, c1 = (((uint32_t)(2 * slot + 1)) ^ sw) << 4;
-        sts128(sbase + OFF_BHI + brow + c0, make_float4(hi[0], hi[1], hi[2], hi[3]));
-        sts128(sbase + OFF_BHI + brow + c1, make_float4(hi[4], hi[5], hi[6], hi[7]));
-        sts128(sbase + OFF_BLO + brow + c0, make_float4(lo[0], lo[1], lo[2], lo[3]));
-        sts128(sbase + OFF_BLO + brow + c1, make_float4(lo[4], lo[5], lo[6], lo[7]));
+      // one batch = 4 channels of this thread's position: blended (fp32, ATen's order; validity as a select -- a branch
+      // here diverges per lane), then written into the operand row.  fp32: hi / lo split, one 16-byte chunk each;
+      // 16-bit: rounded once to T, 8 bytes of the chunk.
+      auto store_batch = [&](const float (&v)[4][4], int slot, int bch, int chan0) {
+        float r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float x = blend(v[c][0], v[c][1], v[c][2], v[c][3], tp);
+          r[c] = (valid && chan0 + c < g.C) ? x : 0.f;
+        }
+        if constexpr (F32) {
+          float h[4], l[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) split_tf32(r[c], h[c], l[c]);
+          const uint32_t ch = (((uint32_t)(2 * slot + bch)) ^ sw) << 4;
+          sts128(sbase + OFF_BHI + brow + ch, make_float4(h[0], h[1], h[2], h[3]));
+          sts128(sbase + OFF_BLO + brow + ch, make_float4(l[0], l[1], l[2], l[3]));
+        } else {
+          const uint32_t ch = ((((uint32_t)(2 * slot + (bch >> 1))) ^ sw) << 4) + (uint32_t)(bch & 1) * 8u;
+          const uint32_t h01 = pack2<T>(r[0], r[1]), h23 = pack2<T>(r[2], r[3]);
+          float l[4];   // residual of the rounding to T (exact in fp32), itself rounded to T
+          l[0] = r[0] - unpack_lo<T>(h01); l[1] = r[1] - unpack_hi<T>(h01);
+          l[2] = r[2] - unpack_lo<T>(h23); l[3] = r[3] - unpack_hi<T>(h23);
+          sts64(sbase + OFF_BHI + brow + ch, h01, h23);
+          sts64(sbase + OFF_BLO + brow + ch, pack2<T>(l[0], l[1]), pack2<T>(l[2], l[3]));
+        }
       };
       if (path == PATH_RAW) {
         // byte offsets of the four taps inside a channel plane of the box (positions without a sample read offset 0)
         const int r0 = (cur.y0 - oy) * RAW_W - ox, r1 = (cur.y1c - oy) * RAW_W - ox;
-        const uint32_t t0 = valid ? (uint32_t)(r0 + cur.x0) << 2 : 0u, t1 = valid ? (uint32_t)(r0 + cur.x1c) << 2 : 0u;
-        const uint32_t t2 = valid ? (uint32_t)(r1 + cur.x0) << 2 : 0u, t3 = valid ? (uint32_t)(r1 + cur.x1c) << 2 : 0u;
-        // Software pipeline over half K steps (4 channels = one 16-byte operand chunk): the 16 tap loads of the next half
-        // step -- across the K-step boundary too, the box is usually there already -- are in flight while this one is
-        // blended, split and stored.  Without it the gather warps, which the barriers keep in lockstep, all load, then all
-        // compute, then all store, and the shared-memory pipe idles half of the time.
-        auto load_half = [&](uint32_t rb, int half, float (&dst)[4][4]) {
+        const uint32_t t0 = valid ? (uint32_t)(r0 + cur.x0) * ES : 0u, t1 = valid ? (uint32_t)(r0 + cur.x1c) * ES : 0u;
+        const uint32_t t2 = valid ? (uint32_t)(r1 + cur.x0) * ES : 0u, t3 = valid ? (uint32_t)(r1 + cur.x1c) * ES : 0u;
+        // Software pipeline over batches of 4 channels: the 16 tap loads of the next batch -- across the K-step boundary
+        // too, the box is usually there already -- are in flight while this one is blended and stored.
+        auto load_batch = [&](uint32_t rb, int bch, float (&dst)[4][4]) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            const uint32_t pl = rb + (uint32_t)(half * 4 + c) * RAW_PLANE;
-            dst[c][0] = lds_f32(pl + t0);
-            dst[c][1] = lds_f32(pl + t1);
-            dst[c][2] = lds_f32(pl + t2);
-            dst[c][3] = lds_f32(pl + t3);
+            const uint32_t pl = rb + (uint32_t)(bch * 4 + c) * RAW_PLANE;
+            dst[c][0] = lds_t<T>(pl + t0);
+            dst[c][1] = lds_t<T>(pl + t1);
+            dst[c][2] = lds_t<T>(pl + t2);
+            dst[c][3] = lds_t<T>(pl + t3);
           }
-        };
-        auto blend_half = [&](const float (&v)[4][4], float4& hi, float4& lo) {
-          float h[4], l[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {   // unconditional blend, validity as a select (a branch here diverges per lane)
-            const float r = blend(v[c][0], v[c][1], v[c][2], v[c][3], tp);
-            split_tf32(valid ? r : 0.f, h[c], l[c]);
-          }
-          hi = make_float4(h[0], h[1], h[2], h[3]);
-          lo = make_float4(l[0], l[1], l[2], l[3]);
         };
         float la[4][4], lb[4][4];
         {
           const int rs = rc % RS, ruse = rc / RS;
           tc_wait(&raw_full[rs], (uint32_t)(ruse & 1));
-          load_half(sbase + OFF_RAW + (uint32_t)rs * RAW_STAGE, 0, la);
+          load_batch(sbase + OFF_RAW + (uint32_t)rs * RAW_STAGE, 0, la);
         }
         for (int ks = 0; ks < nks; ++ks, ++kc, ++rc) {
           const int rs = rc % RS;
           const uint32_t rb = sbase + OFF_RAW + (uint32_t)rs * RAW_STAGE;
-          if (gt == 0 && ks < 4) TC_TRACE(ti, 3 + 3 * ks);
-          load_half(rb, 1, lb);
-          float4 hi, lo;
-          blend_half(la, hi, lo);
           const int slot = kc & (SLOTS - 1), use = kc >> 2;
-          tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
-          if (gt == 0 && ks < 4) TC_TRACE(ti, 4 + 3 * ks);
-          const uint32_t c0 = (((uint32_t)(2 * slot)) ^ sw) << 4, c1 = (((uint32_t)(2 * slot + 1)) ^ sw) << 4;
-          sts128(sbase + OFF_BHI + brow + c0, hi);
-          sts128(sbase + OFF_BLO + brow + c0, lo);
-          if (ks + 1 < nks) {   // first half of the next K step
-            const int rn = (rc + 1) % RS, rnuse = (rc + 1) / RS;
-            tc_wait(&raw_full[rn], (uint32_t)(rnuse & 1));
-            load_half(sbase + OFF_RAW + (uint32_t)rn * RAW_STAGE, 0, la);
+          if (gt == 0 && ks < 4) TC_TRACE(ti, 3 + 3 * ks);
+#pragma unroll
+          for (int bch = 0; bch < NB; ++bch) {
+            float (&cu)[4][4] = (bch & 1) ? lb : la;
+            float (&nx)[4][4] = (bch & 1) ? la : lb;
+            if (bch + 1 < NB) {
+              load_batch(rb, bch + 1, nx);
+            } else if (ks + 1 < nks) {   // first batch of the next K step (NB is even: it lands in `la`)
+              const int rn = (rc + 1) % RS, rnuse = (rc + 1) / RS;
+              tc_wait(&raw_full[rn], (uint32_t)(rnuse & 1));
+              load_batch(sbase + OFF_RAW + (uint32_t)rn * RAW_STAGE, 0, nx);
+            }
+            if (bch == 0) {
+              tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+              if (gt == 0 && ks < 4) TC_TRACE(ti, 4 + 3 * ks);
+            }
+            store_batch(cu, slot, bch, ks * KC + bch * 4);
           }
-          blend_half(lb, hi, lo);
-          sts128(sbase + OFF_BHI + brow + c1, hi);
-          sts128(sbase + OFF_BLO + brow + c1, lo);
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
           __syncwarp();
           if (lane == 0) {
@@ -634,25 +710,24 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         const long long t0 = valid ? r0 + cur.x0 : 0, t1 = valid ? r0 + cur.x1c : 0;
         const long long t2 = valid ? r1 + cur.x0 : 0, t3 = valid ? r1 + cur.x1c : 0;
         for (int ks = 0; ks < nks; ++ks, ++kc) {
-          float tv[KC][4];
+          const int slot = kc & (SLOTS - 1), use = kc >> 2;
 #pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            const T* plane = x2n + (long long)min(ks * KC + c, g.C - 1) * g.x2s[1];
-            tv[c][0] = ldg_f32(plane + t0);
-            tv[c][1] = ldg_f32(plane + t1);
-            tv[c][2] = ldg_f32(plane + t2);
-            tv[c][3] = ldg_f32(plane + t3);
-          }
-          float hi[KC], lo[KC];
+          for (int bch = 0; bch < NB; ++bch) {
+            float tv[4][4];
 #pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            const float r = blend(tv[c][0], tv[c][1], tv[c][2], tv[c][3], tp);
-            split_tf32((valid && ks * KC + c < g.C) ? r : 0.f, hi[c], lo[c]);
+            for (int c = 0; c < 4; ++c) {
+              const T* plane = x2n + (long long)min(ks * KC + bch * 4 + c, g.C - 1) * g.x2s[1];
+              tv[c][0] = ldg_f32(plane + t0);
+              tv[c][1] = ldg_f32(plane + t1);
+              tv[c][2] = ldg_f32(plane + t2);
+              tv[c][3] = ldg_f32(plane + t3);
+            }
+            if (bch == 0) tc_wait(&slot_empty[slot], (uint32_t)((use & 1) ^ 1));
+            store_batch(tv, slot, bch, ks * KC + bch * 4);
           }
-          stage_b(hi, lo, ks);
           fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&b_full[slot_of(kc)]);
+          if (lane == 0) mbar_arrive(&b_full[slot]);
           if (ks == 0 && has_next) nxt = prepare(tile + gridDim.x, ti + 1, nfu, nfv);
         }
       }
@@ -661,10 +736,13 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
   } else if (warp == MMA_WARP) {
     // =========================== MMA issue: one lane ===========================
     if (lane == 0) {
-      // instruction descriptor: D fp32, A / B tf32, both K-major, N = 192, M = 128
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+      // instruction descriptor: D fp32 (bit 4), A / B format (bits 7-9 / 10-12: tf32 = 2; kind::f16: fp16 = 0, bf16 = 1), both
+      // K-major, N = 192, M = 128
+      constexpr uint32_t fmt = F32 ? 2u : (std::is_same<T, __half>::value ? 0u : 1u);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
       const uint64_t d_bh0 = make_desc(sbase + OFF_BHI), d_bh1 = make_desc(sbase + OFF_BHI + NH * 128);
       const uint64_t d_bl0 = make_desc(sbase + OFF_BLO), d_bl1 = make_desc(sbase + OFF_BLO + NH * 128);
+      const uint64_t d_a = make_desc(sbase + OFF_A);                                                     // (16-bit only)
       int kc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
         tc_wait(d_empty, (uint32_t)((ti & 1) ^ 1));   // previous tile drained
@@ -678,13 +756,20 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           if (ks < 4) TC_TRACE(ti, 21 + ks);
           const uint64_t ko = (uint64_t)(2 * slot);   // 32 bytes per K step inside the 128-byte swizzle atom
           const uint32_t acc = ks > 0 ? 1u : 0u;
-          const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
-          umma_tf32_ta(tmem, a_hi, d_bh0 + ko, idesc, acc);
-          umma_tf32_ta(tmem, a_lo, d_bh0 + ko, idesc, 1u);
-          umma_tf32_ta(tmem, a_hi, d_bl0 + ko, idesc, 1u);
-          umma_tf32_ta(tmem + NH, a_hi, d_bh1 + ko, idesc, acc);
-          umma_tf32_ta(tmem + NH, a_lo, d_bh1 + ko, idesc, 1u);
-          umma_tf32_ta(tmem + NH, a_hi, d_bl1 + ko, idesc, 1u);
+          if constexpr (F32) {
+            const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
+            umma_tf32_ta(tmem, a_hi, d_bh0 + ko, idesc, acc);
+            umma_tf32_ta(tmem, a_lo, d_bh0 + ko, idesc, 1u);
+            umma_tf32_ta(tmem, a_hi, d_bl0 + ko, idesc, 1u);
+            umma_tf32_ta(tmem + NH, a_hi, d_bh1 + ko, idesc, acc);
+            umma_tf32_ta(tmem + NH, a_lo, d_bh1 + ko, idesc, 1u);
+            umma_tf32_ta(tmem + NH, a_hi, d_bl1 + ko, idesc, 1u);
+          } else {
+            umma_f16(tmem, d_a + ko, d_bh0 + ko, idesc, acc);
+            umma_f16(tmem, d_a + ko, d_bl0 + ko, idesc, 1u);
+            umma_f16(tmem + NH, d_a + ko, d_bh1 + ko, idesc, acc);
+            umma_f16(tmem + NH, d_a + ko, d_bl1 + ko, idesc, 1u);
+          }
           umma_commit(&slot_empty[slot]);
         }
         umma_commit(d_full);
@@ -710,7 +795,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           ymin = min(ymin, b.z); ymax = max(ymax, b.w);
         }
         mbar_arrive(&bbox_empty[ti & 1]);
-        const int ox = xmin & ~3, oy = ymin;
+        const int ox = xmin & ~(AL - 1), oy = ymin;
         if (xmin <= xmax && xmax - ox < RAW_W && ymax - oy < RAW_H) {
           for (int ks = 0; ks < nks; ++ks, ++rc) {
             const int rs = rc % RS, ruse = rc / RS;
@@ -744,13 +829,14 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 
 bool tc_forward_supported(const Geom& g, int dtype, const UpFlow* uf) {
   if (uf != nullptr && (g.pad != g.md || (g.H & 1) || (g.W & 1))) return false;   // tiles must cover the image exactly once
-  return dtype == CERB_F32 && g.k == 1 && g.s1 == 1 && g.s2 == 1 && (g.md == 4 || g.md == 8) && g.outH > 0 && g.outW > 0;
+  return (dtype == CERB_F32 || dtype == CERB_F16 || dtype == CERB_BF16) && g.k == 1 && g.s1 == 1 && g.s2 == 1 &&
+         (g.md == 4 || g.md == 8) && g.outH > 0 && g.outW > 0;
 }
 
-template <int MDT>
+template <typename T, int MDT>
 static cudaError_t launch_tc_md(const Geom& g, const void* x1, const void* x2, const float* flow, void* out, cudaStream_t stream,
                                 const UpFlow* uf) {
-  using G = tc::Geo<MDT>;
+  using G = tc::Geo<MDT, (int)sizeof(T)>;
   tc::Args a;
   a.g = g;
   a.x1 = x1; a.x2 = x2; a.flow = flow; a.out = out;
@@ -758,7 +844,7 @@ static cudaError_t launch_tc_md(const Geom& g, const void* x1, const void* x2, c
   a.tiles_x = (g.outW + tc::TX - 1) / tc::TX;
   a.tiles_y = (g.outH + tc::TY - 1) / tc::TY;
   a.total_tiles = g.B * a.tiles_x * a.tiles_y * G::NPASS;
-  a.nks = (g.C + tc::KC - 1) / tc::KC;
+  a.nks = (g.C + G::KC - 1) / G::KC;
   a.path_ctr = get_path_counters();
   a.dbg = get_trace_buffer();
   a.cflow = nullptr; a.flow_up = nullptr; a.Hc = a.Wc = 0; a.up_sy = a.up_sx = 0.f;
@@ -773,10 +859,11 @@ static cudaError_t launch_tc_md(const Geom& g, const void* x1, const void* x2, c
   CUtensorMap tm_raw;
   memset(&tm_raw, 0, sizeof(tm_raw));
   a.use_raw = 0;
+  const CUtensorMapDataType dt = std::is_same<T, float>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (std::is_same<T, __half>::value ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   if (!getenv("CERB_DEBUG_TC_NO_RAW"))   // TMA needs 16-byte aligned base / strides (make_tmap_nchw checks)
-    a.use_raw = make_tmap_nchw(&tm_raw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, G::RAW_W, G::RAW_H,
-                               tc::KC, false) ? 1 : 0;
-  auto kern = tc::warp_corr_fwd_tc_kernel<float, MDT>;
+    a.use_raw = make_tmap_nchw(&tm_raw, dt, (int)sizeof(T), x2, g.W, g.H, g.C, g.B, g.x2s, G::RAW_W, G::RAW_H, G::KC, false) ? 1 : 0;
+  auto kern = tc::warp_corr_fwd_tc_kernel<T, MDT>;
   static unsigned long long attr_devs = 0ull;   // function attributes are per device
   {
     int dev = 0;
@@ -810,10 +897,21 @@ static cudaError_t launch_tc_md(const Geom& g, const void* x1, const void* x2, c
   return cudaGetLastError();
 }
 
+template <typename T>
+static cudaError_t launch_tc_t(const Geom& g, const void* x1, const void* x2, const float* flow, void* out, cudaStream_t stream,
+                               const UpFlow* uf) {
+  return g.md == 4 ? launch_tc_md<T, 4>(g, x1, x2, flow, out, stream, uf) : launch_tc_md<T, 8>(g, x1, x2, flow, out, stream, uf);
+}
+
 cudaError_t launch_warp_corr_forward_tc(const Geom& g, int dtype, const void* x1, const void* x2, const float* flow, void* out,
                                         cudaStream_t stream, const UpFlow* uf) {
   if (!tc_forward_supported(g, dtype, uf)) return cudaErrorNotSupported;
-  return g.md == 4 ? launch_tc_md<4>(g, x1, x2, flow, out, stream, uf) : launch_tc_md<8>(g, x1, x2, flow, out, stream, uf);
+  switch (dtype) {
+    case CERB_F32: return launch_tc_t<float>(g, x1, x2, flow, out, stream, uf);
+    case CERB_F16: return launch_tc_t<__half>(g, x1, x2, flow, out, stream, uf);
+    case CERB_BF16: return launch_tc_t<__nv_bfloat16>(g, x1, x2, flow, out, stream, uf);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 }  // namespace cerb

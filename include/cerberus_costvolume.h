@@ -109,8 +109,9 @@ CERB_API int cerb_warp_corr_forward(const cerb_corr_params* p, const void* x1, c
  * variant: 0 auto (what cerb_warp_corr_forward uses), 1 8x32-tile kernel with TMA staging,
  * 2 same without TMA (LDG/STG staging), 3 4x16-tile split-channel kernel with TMA, 4 same
  * without TMA, 5 generic one-thread-per-output kernel, 6 8x16-tile kernel (channels split two ways),
- * 7 tensor-core kernel (tcgen05 / TMEM; fp32 via a 3xTF32 split, max_displacement 4 or 8: what auto picks from 64 tiles of 8x16).
- * Variants 1-4 and 6 need kernel_size=1, stride1=stride2=1, max_displacement>=4, variant 7 additionally fp32 and
+ * 7 tensor-core kernel (tcgen05 / TMEM; fp32 via a 3xTF32 split, fp16 / bf16 via kind::f16; max_displacement 4 or 8: what auto
+ * picks from 64 tiles of 8x16).
+ * Variants 1-4 and 6 need kernel_size=1, stride1=stride2=1, max_displacement>=4, variant 7 additionally
  * max_displacement 4 or 8 (else CERB_EUNSUPPORTED / cudaErrorNotSupported). */
 CERB_API int cerb_warp_corr_forward_variant(const cerb_corr_params* p, const void* x1, const void* x2,
                                             const float* flow, void* out, int variant, cerb_stream_t stream);

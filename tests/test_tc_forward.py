@@ -75,6 +75,28 @@ def test_tc_forward_md8_vs_oracle(B, C, H, W, pad, sigma):
     assert rel_err(out.cpu().numpy(), ref) < TOL
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 6e-4), (torch.bfloat16, 5e-3)])
+@pytest.mark.parametrize("B,C,H,W,pad,md,sigma", [
+    (2, 32, 24, 64, 4, 4, 1.5),
+    (1, 64, 40, 96, 4, 4, 1.5),     # 64 channels = one full 128-byte operand row (4 K steps of 16)
+    (2, 20, 19, 37, 4, 4, 2.5),     # ragged: no TMA, partial K step
+    (1, 48, 32, 64, 8, 8, 1.5),     # max_displacement 8
+    (1, 24, 30, 52, 2, 4, 12.0),    # pad < md, direct gather
+    (1, 96, 16, 48, 4, 4, None),    # no flow
+])
+def test_tc_forward_16bit_vs_oracle(dtype, tol, B, C, H, W, pad, md, sigma):
+    """fp16 / bf16 inputs on the tensor cores (kind::f16; the blended x2w as hi + lo in T, two products): the only error
+    against an exact evaluation on the same 16-bit inputs is the rounding of the stored result (2^-11 / 2^-8 of max|ref|)."""
+    x1, x2, fl = case(B * 10 + C + md, B, C, H, W, sigma)
+    t1 = torch.from_numpy(x1).to(dev()).to(dtype)
+    t2 = torch.from_numpy(x2).to(dev()).to(dtype)
+    tf = torch.from_numpy(fl).to(dev()) if fl is not None else None
+    ref = co.level_forward(t1.float().cpu().numpy(), t2.float().cpu().numpy(), fl, pad, 1, md, 1, 1, co.WARP_TORCH, 0.1)
+    out = ops.warp_corr_forward(t1, t2, tf, pad, 1, md, 1, 1, 1, cb.WARP_TORCH, 0.1, variant=TC)
+    assert out.dtype == dtype
+    assert rel_err(out.float().cpu().numpy(), ref) < tol
+
+
 def test_tc_forward_no_activation_and_roll():
     x1, _, fl = case(5, 4, 40, 32, 80, 2.0)
     f = torch.from_numpy(x1).to(dev())
