@@ -50,7 +50,7 @@ DIRS = 2      # flow directions per step (forward and backward flow of the pair)
 N_SETS = 6    # 6 x 58.7 MB of inputs+outputs = 352 MB > 2 x 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the finest-level kernel (both directions), from this
 # round's `ncu --set full` capture summarised in profiles/r02_ncu_fwd_finest_level.txt
-NCU_TRAFFIC_BYTES_FINEST = 9238016   # 9.236 MB read + 2 KB written (the 21.2 MB of output is still dirty in L2 at kernel end)
+NCU_TRAFFIC_BYTES_FINEST = 9004288   # 9.003 MB read + 1 KB written (the 21.2 MB of output is still dirty in L2 at kernel end)
 NCU_TRAFFIC_SOURCE = "profiles/r02_ncu_fwd_finest_level.txt"
 
 
