@@ -431,6 +431,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 #pragma unroll
             for (int dx = 0; dx < D; ++dx) {
               const float res = __fmul_rn(__uint_as_float(v[dx]), rC);
+#ifdef CERB_TCX_NOSTG
+              if (res == 123.456f)
+#endif
               *orow = from_f32<T>(res > 0.f ? res : res * act_slope);
               orow += os1;
             }
@@ -455,7 +458,11 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
         // two halo rows per iteration: their select networks and stores are independent instruction streams (one warp
         // per sub-partition drains at a time -- what it lacks is instruction-level parallelism, not issue slots)
 #pragma unroll 1
+#ifdef CERB_TCX_NODRAIN
+        for (int r = rr1 - 2; r < rr1; r += 2) {
+#else
         for (int r = rr0; r < rr1; r += 2) {
+#endif
           uint32_t v0[24], v1[24];
           const uint32_t col = (uint32_t)((r - pass * HYB) * HX);
           tmem_ld8(tlane + col, v0);
@@ -637,8 +644,12 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 #pragma unroll
           for (int c = 0; c < 4; ++c) split_tf32(r[c], h[c], l[c]);
           const uint32_t ch = (((uint32_t)(2 * slot + bch)) ^ sw) << 4;
+#ifdef CERB_TCX_NOSTS
+          if (h[0] == 123.456f) sts128(sbase + OFF_BHI + brow + ch, make_float4(h[0], h[1], l[2], l[3]));
+#else
           sts128(sbase + OFF_BHI + brow + ch, make_float4(h[0], h[1], h[2], h[3]));
           sts128(sbase + OFF_BLO + brow + ch, make_float4(l[0], l[1], l[2], l[3]));
+#endif
         } else {
           const uint32_t ch = ((((uint32_t)(2 * slot + (bch >> 1))) ^ sw) << 4) + (uint32_t)(bch & 1) * 8u;
           const uint32_t h01 = pack2<T>(r[0], r[1]), h23 = pack2<T>(r[2], r[3]);
@@ -660,10 +671,15 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint32_t pl = rb + (uint32_t)(bch * 4 + c) * RAW_PLANE;
+#ifdef CERB_TCX_NOLDS   // CERB_TCX_*: timing-only elimination builds (tools/ab_variants.py), results are wrong
+            dst[c][0] = __uint_as_float(pl + t0); dst[c][1] = __uint_as_float(pl + t1);
+            dst[c][2] = __uint_as_float(pl + t2); dst[c][3] = __uint_as_float(pl + t3);
+#else
             dst[c][0] = lds_t<T>(pl + t0);
             dst[c][1] = lds_t<T>(pl + t1);
             dst[c][2] = lds_t<T>(pl + t2);
             dst[c][3] = lds_t<T>(pl + t3);
+#endif
           }
         };
         float la[4][4], lb[4][4];
@@ -694,7 +710,9 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
             }
             store_batch(cu, slot, bch, ks * KC + bch * 4);
           }
+#ifndef CERB_TCX_NOFENCE
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+#endif
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&raw_empty[rs]);
@@ -756,6 +774,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
           if (ks < 4) TC_TRACE(ti, 21 + ks);
           const uint64_t ko = (uint64_t)(2 * slot);   // 32 bytes per K step inside the 128-byte swizzle atom
           const uint32_t acc = ks > 0 ? 1u : 0u;
+#ifndef CERB_TCX_NOMMA
           if constexpr (F32) {
             const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
             umma_tf32_ta(tmem, a_hi, d_bh0 + ko, idesc, acc);
@@ -770,6 +789,7 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
             umma_f16(tmem + NH, d_a + ko, d_bh1 + ko, idesc, acc);
             umma_f16(tmem + NH, d_a + ko, d_bl1 + ko, idesc, 1u);
           }
+#endif
           umma_commit(&slot_empty[slot]);
         }
         umma_commit(d_full);
