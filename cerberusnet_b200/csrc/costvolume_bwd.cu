@@ -21,6 +21,11 @@
 namespace cerb {
 
 long long* get_trace_buffer();
+// tensor-core backward (costvolume_bwd_tc.cu)
+bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long long s0s[3], const void* x1);
+cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long long s0s[3], int s0_roll, const void* x1,
+                                    const void* x2, const float* flow, const void* out, const void* gout, void* gx1,
+                                    void* gsecond, void* gx2_splat, float* gflow, cudaStream_t stream);
 #define BWD_TRACE(slot) do { if (a.dbg && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && threadIdx.x == 0) a.dbg[(slot)] = clock64(); } while (0)
 
 constexpr int kMDb = 4;
@@ -730,6 +735,26 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     static const int force_ty = getenv("CERB_DEBUG_BWD_TY") ? atoi(getenv("CERB_DEBUG_BWD_TY")) : 0;
     static const bool unfused = getenv("CERB_DEBUG_BWD_UNFUSED") != nullptr;
     const bool ty4 = force_ty ? force_ty == 4 : true;
+    // Tensor-core kernel (costvolume_bwd_tc.cu): fp32, md = pad = 4, C <= 128, 16-byte aligned rows; from 64 tiles of 8 x 16 up
+    // (CERB_DEBUG_BWD_TC=1 forces it wherever it is supported, =0 turns it off)
+    if (std::is_same<T, float>::value && !unfused && !force_ty) {
+      static const int tc_mode = getenv("CERB_DEBUG_BWD_TC") ? atoi(getenv("CERB_DEBUG_BWD_TC")) : -1;
+      const long long s0s[3] = {a.s_ns[0], a.s_cs[0], a.s_hs[0]};
+      const long long tiles = (long long)g.B * ((g.H + 7) / 8) * ((g.W + 15) / 16);
+      if (tc_mode != 0 && (tc_mode == 1 || tiles >= 64) && tc_backward_supported(g, CERB_F32, a.s[0], s0s, x1)) {
+        if (flow != nullptr) {
+          e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
+          if (e != cudaSuccess) return e;
+        }
+        e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, x2, flow, out, gout, gx1, flow ? nullptr : gx2,
+                                    flow ? gx2 : nullptr, gflow, stream);
+        if (e == cudaSuccess) {
+          count_launches(flow != nullptr ? 3 : 1);
+          return cudaGetLastError();
+        }
+        if (e != cudaErrorNotSupported) return e;
+      }
+    }
     if (!unfused && ty4) {
       // one kernel for both gradients.  With a flow the second one is splatted through the bilinear taps straight into
       // grad_x2 (zeroed here; 16-bit: an fp32 accumulator in the workspace, narrowed once) and reduced into grad_flow
