@@ -154,6 +154,8 @@ def lib() -> ctypes.CDLL:
     L.cerb_trt_warp_corr_deserialize.argtypes = [vp, ctypes.c_size_t, wfp]
     L.cerb_debug_set_path_counters.argtypes = [vp]
     L.cerb_debug_set_path_counters.restype = None
+    L.cerb_debug_set_backward_kernel.argtypes = [ctypes.c_int]
+    L.cerb_debug_set_backward_kernel.restype = None
     if L.cerb_abi_version() != 1:
         raise RuntimeError("libcerberus_costvolume.so: ABI version mismatch")
     _lib = L

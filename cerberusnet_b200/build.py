@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_NAME = "libcerberus_costvolume.so"
 LIB_PATH = os.path.join(HERE, LIB_NAME)
-SOURCES = ["costvolume_fwd.cu", "costvolume_fwd_tc.cu", "costvolume_bwd.cu", "costvolume_bwd_tc.cu", "costvolume_api.cu", "costvolume_sampler.cu", "photometric.cu"]
+SOURCES = ["costvolume_fwd.cu", "costvolume_fwd_tc.cu", "costvolume_bwd.cu", "costvolume_bwd_tc.cu", "costvolume_splat.cu", "costvolume_api.cu", "costvolume_sampler.cu", "photometric.cu"]
 HEADERS = ["costvolume_common.cuh", "costvolume_launch.h",
            os.path.join("..", "..", "include", "cerberus_costvolume.h"),
            os.path.join("..", "..", "include", "cerberus_trt_plugin.h")]

@@ -328,6 +328,8 @@ CERB_API void cerb_debug_set_trace_iter(int it) { cerb::set_trace_iter(it); }
 // dev_ptr: 4 x uint64 on the device, zeroed by the caller: tiles per staging path of the warped forward
 // ([1] small raw box, [3] large raw box, [2] direct-gather fallback); NULL switches counting off.
 CERB_API void cerb_debug_set_path_counters(void* dev_ptr) { cerb::set_path_counters((unsigned long long*)dev_ptr); }
+// which kernel cerb_warp_corr_backward's fast path takes: -1 automatic (default), 0 CUDA cores, 1 tensor cores wherever supported
+CERB_API void cerb_debug_set_backward_kernel(int mode) { cerb::set_backward_kernel_mode(mode); }
 
 int cerb_measure_fma_peak(double* tflops, cerb_stream_t stream) {
   if (!tflops) return CERB_EINVAL;

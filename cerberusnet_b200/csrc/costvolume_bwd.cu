@@ -25,7 +25,15 @@ long long* get_trace_buffer();
 bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long long s0s[3], const void* x1);
 cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long long s0s[3], int s0_roll, const void* x1,
                                     const void* x2, const float* flow, const void* out, const void* gout, void* gx1,
-                                    void* gsecond, void* gx2_splat, float* gflow, cudaStream_t stream);
+                                    void* gsecond, int gsecond_roll, void* gx2_splat, float* gflow, cudaStream_t stream);
+// which backward kernel the fast path takes: -1 automatic, 0 CUDA cores only, 1 tensor cores wherever supported
+// (initialised from CERB_DEBUG_BWD_TC; cerb_debug_set_backward_kernel for tests and the bench)
+static int g_bwd_tc_mode = -2;
+int get_backward_kernel_mode() {
+  if (g_bwd_tc_mode == -2) g_bwd_tc_mode = getenv("CERB_DEBUG_BWD_TC") ? atoi(getenv("CERB_DEBUG_BWD_TC")) : -1;
+  return g_bwd_tc_mode;
+}
+void set_backward_kernel_mode(int mode) { g_bwd_tc_mode = mode < -1 || mode > 1 ? -1 : mode; }
 #define BWD_TRACE(slot) do { if (a.dbg && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 0 && threadIdx.x == 0) a.dbg[(slot)] = clock64(); } while (0)
 
 constexpr int kMDb = 4;
@@ -645,6 +653,31 @@ __global__ void __launch_bounds__(256) cvt_from_f32_kernel(const float* __restri
 }
 
 // ------------------------------------------------------------------ host launchers -------
+// flow_warp backward through shared-memory windows (costvolume_splat.cu), fp32
+cudaError_t launch_flow_warp_backward_box(const float* img, const long long in_s[3], const float* flow, const long long f_s[3],
+                                          const float* gout, float* gimg, float* gflow, int B, int C, int H, int W, int mode,
+                                          int roll, cudaStream_t stream);
+static int grid_for(long long total, int block);
+// splat of a gradient wrt the warped map (contiguous, x1's batch order) into a zeroed grad_image + the flow gradient: the
+// shared-memory-window kernel for fp32 when the tensors can be TMA tensors, scattered atomics otherwise
+template <typename T, typename GT>
+__global__ void flow_warp_bwd_kernel(const T* __restrict__ img, long long in_ns, long long in_cs, long long in_hs,
+                                     const float* __restrict__ flow, long long f_ns, long long f_cs, long long f_hs,
+                                     const T* __restrict__ gout, GT* __restrict__ gimg, float* __restrict__ gflow, int B, int C,
+                                     int H, int W, int mode, int roll);
+template <typename T, typename GT>
+static cudaError_t splat_backward(const T* img, long long in_ns, long long in_cs, long long in_hs, const float* flow, long long f_ns,
+                                  long long f_cs, long long f_hs, const T* gout, GT* gimg, float* gflow, int B, int C, int H, int W,
+                                  int mode, int roll, cudaStream_t stream) {
+  if constexpr (std::is_same<T, float>::value && std::is_same<GT, float>::value) {
+    const long long in_s[3] = {in_ns, in_cs, in_hs}, f_s[3] = {f_ns, f_cs, f_hs};
+    const cudaError_t e = launch_flow_warp_backward_box(img, in_s, flow, f_s, gout, gimg, gflow, B, C, H, W, mode, roll, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  flow_warp_bwd_kernel<T, GT><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(img, in_ns, in_cs, in_hs, flow, f_ns, f_cs, f_hs,
+                                                                                        gout, gimg, gflow, B, C, H, W, mode, roll);
+  return cudaGetLastError();
+}
 static int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -738,7 +771,7 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     // Tensor-core kernel (costvolume_bwd_tc.cu): fp32, md = pad = 4, C <= 128, 16-byte aligned rows; from 64 tiles of 8 x 16 up
     // (CERB_DEBUG_BWD_TC=1 forces it wherever it is supported, =0 turns it off)
     if (std::is_same<T, float>::value && !unfused && !force_ty) {
-      static const int tc_mode = getenv("CERB_DEBUG_BWD_TC") ? atoi(getenv("CERB_DEBUG_BWD_TC")) : -1;
+      const int tc_mode = get_backward_kernel_mode();
       const long long s0s[3] = {a.s_ns[0], a.s_cs[0], a.s_hs[0]};
       const long long tiles = (long long)g.B * ((g.H + 7) / 8) * ((g.W + 15) / 16);
       if (tc_mode != 0 && (tc_mode == 1 || tiles >= 64) && tc_backward_supported(g, CERB_F32, a.s[0], s0s, x1)) {
@@ -746,8 +779,20 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
           e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
           if (e != cudaSuccess) return e;
         }
+        static const bool fused_splat = getenv("CERB_DEBUG_BWD_TC_BOX") != nullptr;
+        if (flow != nullptr && !fused_splat) {
+          // gradient wrt the warped map into the workspace (coalesced stores), then the splat as its own kernel
+          e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, x2, nullptr, out, gout, gx1, gwarped, 0, nullptr, nullptr, stream);
+          if (e == cudaSuccess) {
+            e = splat_backward<T, T>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
+                g.C, g.H, g.W, g.warp_mode, g.x2roll, stream);
+        if (e != cudaSuccess) return e;
+            count_launches(4);
+            return cudaGetLastError();
+          }
+        } else
         e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, x2, flow, out, gout, gx1, flow ? nullptr : gx2,
-                                    flow ? gx2 : nullptr, gflow, stream);
+                                    g.x2roll, flow ? gx2 : nullptr, gflow, stream);
         if (e == cudaSuccess) {
           count_launches(flow != nullptr ? 3 : 1);
           return cudaGetLastError();
@@ -796,16 +841,16 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
         float* acc32 = reinterpret_cast<float*>(gwarped + in_elems);
         e = cudaMemsetAsync(acc32, 0, (size_t)in_elems * sizeof(float), stream);
         if (e != cudaSuccess) return e;
-        flow_warp_bwd_kernel<T, float><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-            (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, acc32, gflow, g.B,
-            g.C, g.H, g.W, g.warp_mode, g.x2roll);
+        e = splat_backward<T, float>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, acc32, gflow, g.B,
+            g.C, g.H, g.W, g.warp_mode, g.x2roll, stream);
+        if (e != cudaSuccess) return e;
         cvt_from_f32_kernel<T><<<grid_for(in_elems, 256), 256, 0, stream>>>(acc32, (T*)gx2, in_elems);
       } else {
         e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
         if (e != cudaSuccess) return e;
-        flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-            (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
-            g.C, g.H, g.W, g.warp_mode, g.x2roll);
+        e = splat_backward<T, T>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
+            g.C, g.H, g.W, g.warp_mode, g.x2roll, stream);
+        if (e != cudaSuccess) return e;
       }
     }
     count_launches(flow != nullptr ? (sizeof(T) == 2 ? 6 : 5) : 2);
@@ -830,9 +875,9 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
       (const T*)out, (T*)gx1, gwarped, 0);
   e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
   if (e != cudaSuccess) return e;
-  flow_warp_bwd_kernel<T, T><<<grid_for((long long)g.B * g.H * g.W, 256), 256, 0, stream>>>(
-      (const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B, g.C,
-      g.H, g.W, g.warp_mode, g.x2roll);
+  e = splat_backward<T, T>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B, g.C,
+      g.H, g.W, g.warp_mode, g.x2roll, stream);
+        if (e != cudaSuccess) return e;
   count_launches(4);
   return cudaGetLastError();
 }
@@ -874,9 +919,9 @@ static cudaError_t warp_bwd_t(const void* image, const float* flow, const void* 
   cudaError_t e = cudaMemsetAsync(gimage, 0, (size_t)B * C * H * W * sizeof(T), stream);
   if (e != cudaSuccess) return e;
   const long long cs = (long long)H * W;
-  flow_warp_bwd_kernel<T, T><<<grid_for((long long)B * H * W, 256), 256, 0, stream>>>(
-      (const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (const T*)gout, (T*)gimage,
-      gflow, B, C, H, W, mode, 0);
+  e = splat_backward<T, T>((const T*)image, (long long)C * cs, cs, (long long)W, flow, 2 * cs, cs, (long long)W, (const T*)gout, (T*)gimage,
+      gflow, B, C, H, W, mode, 0, stream);
+        if (e != cudaSuccess) return e;
   count_launches(2);
   return cudaGetLastError();
 }

@@ -23,8 +23,9 @@
 //     band chunks -> stage the next tile's Gx -> drain the accumulator (tcgen05.ld): grad_x1 is stored, the gradient with
 //     respect to the second input is either stored (no flow) or pushed through the four bilinear taps of its position into
 //     grad_x2 (red.global.add) with the flow gradient accumulated over the channels.
-// Roles: warps 0-3 gradient wrt x1, 4-7 gradient wrt the second input, 8-11 operand split, 12 MMA issue (one lane),
-// 13 TMA issue (one lane).  One CTA per SM, persistent over tiles.
+// Roles (16 warps): 0-3 gradient wrt x1, 4-7 gradient wrt the second input; per gradient one operand-split warp (8-9), one
+// TMA-issue lane (10-11) and two MMA-issue lanes (12-15).  The two gradients' pipelines are independent of each other and
+// run half a tile period apart.  One CTA per SM, persistent over tiles.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -38,6 +39,8 @@ namespace cerb {
 bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
                     const long long strides[3], int bx, int by, int bc, bool swizzle128);
 int num_sms_current();
+unsigned long long* get_path_counters();
+long long* get_trace_buffer();
 
 namespace btc {
 
@@ -46,15 +49,25 @@ constexpr int MD = 4, D = 9, D2 = 81;
 constexpr int HY = TY + 2 * MD;                 // 16 halo rows = band chunks per tile and gradient
 constexpr int KU = TX + 2 * MD;                 // 24 K columns per chunk (3 MMAs of K = 8)
 constexpr int KBOX = 32;                        // TMA box width: one 128-byte swizzle row per channel
-constexpr int GROUP_WARPS = 4, SPLIT_WARPS = 4;
-constexpr int MMA_WARP = 2 * GROUP_WARPS + SPLIT_WARPS, TMA_WARP = MMA_WARP + 1;
-constexpr int NTHREADS = (TMA_WARP + 1) * 32;   // 448
+constexpr int GROUP_WARPS = 4, SPLIT_WARPS = 2, TMA_WARPS = 2, MMA_WARPS = 4;   // per gradient: one split, one TMA, two MMA-issue warps
+static_assert(SPLIT_WARPS % 2 == 0, "split warps alternate between the two gradients");
+constexpr int TMA_WARP = 2 * GROUP_WARPS + SPLIT_WARPS, MMA_WARP = TMA_WARP + TMA_WARPS;
+constexpr int NTHREADS = (MMA_WARP + MMA_WARPS) * 32;   // 512: 16 warps (registers are allocated per 4 warps: 128 per thread)
 constexpr int PADPL = 3;                        // zero planes before / after the 81 of a Gx buffer (shifted reads)
 constexpr int GPLANES = D2 + 2 * PADPL;
 constexpr uint32_t GS_BYTES = GPLANES * M * 4;  // 44544
-constexpr int MAXSTG = 4, MAXSLOT = 4;
+constexpr int MAXSTG = 6, MAXSLOT = 4;
 constexpr int SLOT_COLS = 2 * KU;               // band slot in TMEM: 24 hi + 24 lo columns
-constexpr int NBARS = 2 * (3 * MAXSTG + 2 * MAXSLOT + 2);
+constexpr int NBARS = 2 * (3 * MAXSTG + 2 * MAXSLOT + 2) + 2;   // + the splat's x2-box barrier, + the groups' phase offset
+// splat through shared memory: the taps of a tile's 128 positions land in a BOX_H x BOX_W window of grad_x2 when the flow
+// varies by at most +-SPLAT_MARGIN px inside the tile; CB channels per pass: x2 window in by TMA (tap values for the flow
+// gradient), gradient window accumulated with shared-memory reductions and added to grad_x2 by one TMA reduce
+// (tools/microbench/atomics.cu: scattered red.global 246 G/s = 205 us for this level, coalesced reductions 4 TB/s)
+constexpr int SPLAT_MARGIN = 6, CB = 8;
+constexpr int BOX_H = TY + 2 * SPLAT_MARGIN + 2;                       // 22
+constexpr int BOX_W = (TX + 2 * SPLAT_MARGIN + 2 + 3 + 3) / 4 * 4;     // 36: origin aligned down to 4 elements
+constexpr uint32_t BOX_BYTES = CB * BOX_H * BOX_W * 4;                 // 25344
+static_assert(BOX_BYTES % 128 == 0, "TMA shared-memory alignment");
 
 struct Args {
   Geom g;
@@ -68,8 +81,20 @@ struct Args {
   float* gflow;
   int tiles_x, tiles_y, total_tiles;
   int npad, nstg, nslot;  // N of the MMA, operand stages per gradient, band slots per gradient
+  int nacc;               // partial accumulators per gradient (1..3)
+  int g2_roll;            // no flow: batch roll applied when writing gsecond (x2_batch_roll when it is grad_x2 itself)
   int s0_roll;            // batch roll applied to the TMA item coordinate of the first gradient's S (x2 itself when no flow)
+  int use_pf;             // tensor maps tm_go / tm_o valid: the next tile's grad_out / out planes are prefetched into L2
+  int use_box;            // splat through shared-memory windows (tensor maps tm_x2 / tm_gx2 valid, 3 boxes in shared memory)
+  long long* dbg;         // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer; -DCERB_BTC_TRACE), 192 slots per CTA
+  unsigned long long* path_ctr;   // [1] tiles splatted through the box, [2] tiles on the direct path (cerb_debug_set_path_counters)
 };
+
+#ifdef CERB_BTC_TRACE
+#define BT_TRACE(ti, s) do { if (a.dbg && (ti) < 4) a.dbg[(long long)blockIdx.x * 192 + 1 + (ti) * 40 + (s)] = clock64(); } while (0)
+#else
+#define BT_TRACE(ti, s) do { } while (0)
+#endif
 
 // ---- tcgen05 wrappers (same encodings as costvolume_fwd_tc.cu, validated in tools/microbench/umma_probe.cu)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {   // K-major, SWIZZLE_128B, 8-row atoms 1024 bytes apart
@@ -81,6 +106,13 @@ __device__ __forceinline__ void umma_tf32_ta(uint32_t d_tmem, uint32_t a_tmem, u
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -110,6 +142,22 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {   //
 }
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) { mbar_wait_hint(bar, parity, 20000); }
 __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+// shared-memory fp32 atomics are compare-and-swap loops (SASS ATOMS.CAST.SPIN: measured 18 K cycles per pass of 4096 here);
+// 32-bit integer ones are native (ATOMS.ADD): the gradient window is accumulated in fixed point -- scale = a power of two
+// chosen from the tile's largest contribution so that 128 of them cannot overflow, i.e. 2^-23 of that contribution per
+// term, far inside the fp32 parity bar -- and converted in place before the TMA reduce.  Integer sums are associative:
+// the window is bit-reproducible whatever the order of the reductions.
+__device__ __forceinline__ void red_shared_s32(uint32_t addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {   // tile -> L2
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// TMA: 4-D tiled reduction shared -> global, element-wise add (SASS: UTMAREDG); out-of-range elements are clipped
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 
 // TMEM lane (= MMA row) of tile position (py, px): a warp's 32 lanes are 8 rows x 4 columns
 __device__ __forceinline__ int lane_of_pos(int py, int px) { return 32 * (px >> 2) + 4 * py + (px & 3); }
@@ -118,15 +166,18 @@ __device__ __forceinline__ int lane_of_pos(int py, int px) { return 32 * (px >> 
 __device__ __forceinline__ int plane_idx(int t) { return (t & ~31) | ((t + 8 * (t >> 5)) & 31); }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, const __grid_constant__ CUtensorMap tm_s1) {
+corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, const __grid_constant__ CUtensorMap tm_s1,
+                   const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_gx2,
+                   const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_o) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(smem);
   const Geom& g = a.g;
-  const int npad = a.npad, nstg = a.nstg, nslot = a.nslot;
+  const int npad = a.npad, nstg = a.nstg, nslot = a.nslot, nacc = a.nacc;
   const uint32_t STG = (uint32_t)npad * 128u;                       // one operand tile (hi or lo) of a chunk
   const uint32_t OFF_GS = 2u * (uint32_t)nstg * 2u * STG;           // Gx buffers of the two groups
-  const uint32_t OFF_BAR = OFF_GS + 2u * GS_BYTES;
+  const uint32_t OFF_BOX = OFF_GS + 2u * GS_BYTES;                  // x2 window, two gradient windows (use_box)
+  const uint32_t OFF_BAR = OFF_BOX + (a.use_box ? 3u * BOX_BYTES : 0u);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
   // per gradient X: raw_full[MAXSTG] s_full[MAXSTG] s_empty[MAXSTG] band_full[MAXSLOT] band_empty[MAXSLOT] d_full d_empty
   auto BAR = [&](int X, int which, int i) -> uint64_t* {
@@ -135,24 +186,34 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
     return bars + base + (which < 5 ? off + i : 3 * MAXSTG + 2 * MAXSLOT + (which - 5));
   };
   enum { RAW_FULL = 0, S_FULL = 1, S_EMPTY = 2, BAND_FULL = 3, BAND_EMPTY = 4, D_FULL = 5, D_EMPTY = 6 };
+  uint64_t* xb_full = bars + NBARS - 1;
+  uint64_t* offset_bar = bars + NBARS - 2;
   uint32_t* tmem_slot = (uint32_t*)(smem + OFF_BAR + NBARS * 8);
+  int* bbox_red = (int*)(smem + OFF_BAR + NBARS * 8 + 24);   // [4 warps][xmin, xmax, ymin, ymax]
+  uint32_t* amax_red = (uint32_t*)(smem + OFF_BAR + NBARS * 8 + 24 + 64);   // [4 warps] largest |gradient| of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int X = 0; X < 2; ++X) {
       for (int s = 0; s < MAXSTG; ++s) {
         mbar_init(BAR(X, RAW_FULL, s), 1);
-        mbar_init(BAR(X, S_FULL, s), SPLIT_WARPS);
-        mbar_init(BAR(X, S_EMPTY, s), 1);
+        mbar_init(BAR(X, S_FULL, s), 1);
+        mbar_init(BAR(X, S_EMPTY, s), min(nacc, 2));
       }
       for (int s = 0; s < MAXSLOT; ++s) {
         mbar_init(BAR(X, BAND_FULL, s), GROUP_WARPS);
-        mbar_init(BAR(X, BAND_EMPTY, s), 1);
+        mbar_init(BAR(X, BAND_EMPTY, s), min(nacc, 2));
       }
-      mbar_init(BAR(X, D_FULL, 0), 1);
+      mbar_init(BAR(X, D_FULL, 0), min(nacc, 2));
       mbar_init(BAR(X, D_EMPTY, 0), GROUP_WARPS);
     }
+    mbar_init(xb_full, 1);
+    mbar_init(offset_bar, GROUP_WARPS);
     fence_barrier_init();
+    if (a.use_box) {
+      tma_prefetch_desc(&tm_x2);
+      tma_prefetch_desc(&tm_gx2);
+    }
     tma_prefetch_desc(&tm_s0);
     tma_prefetch_desc(&tm_s1);
   }
@@ -166,7 +227,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t RING0 = 2u * (uint32_t)npad;   // TMEM columns: accumulators [0, npad) and [npad, 2 npad), then the band rings
+  const uint32_t RING0 = 2u * (uint32_t)(nacc * npad);   // TMEM columns: 2 x nacc accumulators of npad columns, then the band rings
   if (warp < GROUP_WARPS) {
     // band columns a lane never writes must read as zero: clear both rings once (warp w owns lane quadrant w)
     const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16) + RING0;
@@ -177,6 +238,9 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
   __syncthreads();
   tc_fence_after();
 
+#ifdef CERB_BTC_TRACE
+  if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 192] = clock64();
+#endif
   const int per_img = a.tiles_x * a.tiles_y;
   auto decode = [&](int tile, int& n, int& y0, int& x0) {
     n = tile / per_img;
@@ -210,24 +274,41 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
       const float* go = a.gout + (long long)n * g.os[0];
       const float* oo = mask ? a.out + (long long)n * g.os[0] : go;
       const int qy = y0 + spy, qx = x0 + spx;
+      const int os1 = (int)g.os[1], os2 = (int)g.os[2];   // (the launcher checks that an item's 81 planes fit 31 bits)
+      // Entry e = (ey, ex) reads plane e at the position itself (X == 0) or plane (8 - ey, 8 - ex) at position q + e - 4
+      // (X == 1).  The address splits into a row part and a column part; loads are unconditional from clamped (always
+      // valid) addresses and validity is applied afterwards (costvolume_bwd.cu: predicated loads serialise).
+      int xo[D];
+      unsigned colok = 0, rowok = 0;
+#pragma unroll
+      for (int e = 0; e < D; ++e) {
+        const int px = X == 0 ? qx : qx + e - MD, py = X == 0 ? qy : qy + e - MD;
+        xo[e] = (X == 0 ? e : -e) * os1 + min(max(px, 0), g.outW - 1);
+        if (px >= 0 && px < g.outW) colok |= 1u << e;
+        if (py >= 0 && py < g.outH) rowok |= 1u << e;
+      }
 #pragma unroll 1
       for (int ey0 = 0; ey0 < D; ey0 += 3) {
         float gv[3 * D], ov[3 * D];
-        // unconditional loads from clamped addresses, validity applied afterwards (costvolume_bwd.cu: predicated loads serialise)
 #pragma unroll
-        for (int r = 0; r < 3 * D; ++r) {
-          const int ey = ey0 + r / D, ex = r % D;
-          const int py = X == 0 ? qy : qy + ey - MD, px = X == 0 ? qx : qx + ex - MD;
-          const int d = X == 0 ? ey * D + ex : (D - 1 - ey) * D + (D - 1 - ex);
-          const long long o = (long long)d * g.os[1] + (long long)min(max(py, 0), g.outH - 1) * g.os[2] + min(max(px, 0), g.outW - 1);
-          gv[r] = __ldcg(go + o);
-          ov[r] = __ldcg(oo + o);
+        for (int r3 = 0; r3 < 3; ++r3) {
+          const int ey = ey0 + r3;
+          const int py = X == 0 ? qy : qy + ey - MD;
+          const int rb = (X == 0 ? ey * D : (D - 1 - ey) * D + D - 1) * os1 + min(max(py, 0), g.outH - 1) * os2;
+#pragma unroll
+          for (int ex = 0; ex < D; ++ex) {
+#ifdef CERB_BTC_X_NOSTAGE
+            gv[r3 * D + ex] = __int_as_float(rb + xo[ex]);
+            ov[r3 * D + ex] = __int_as_float(rb - xo[ex]);
+#else
+            gv[r3 * D + ex] = __ldcg(go + (rb + xo[ex]));
+            ov[r3 * D + ex] = __ldcg(oo + (rb + xo[ex]));
+#endif
+          }
         }
 #pragma unroll
         for (int r = 0; r < 3 * D; ++r) {
-          const int ey = ey0 + r / D, ex = r % D;
-          const int py = X == 0 ? qy : qy + ey - MD, px = X == 0 ? qx : qx + ex - MD;
-          const bool ok = py >= 0 && py < g.outH && px >= 0 && px < g.outW;
+          const bool ok = ((rowok >> (ey0 + r / D)) & (colok >> (r % D)) & 1u) != 0u;
           float v = ok ? gv[r] : 0.f;
           if (mask && !(ov[r] > 0.f)) v *= slope;
           Gs[(PADPL + ey0 * D + r) * M + sidx] = v;
@@ -237,9 +318,17 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
 
     int cnt = 0;   // band chunks built so far (all tiles)
     int ti = 0;
+    int xcnt = 0, gcnt = 0;   // x2 windows loaded / gradient windows reduced so far (splat)
     if ((int)blockIdx.x < a.total_tiles) stage_g(blockIdx.x);
     named_bar_sync(bar_id, 128);
+#ifndef CERB_BTC_NO_OFFSET
+    // The two groups run half a period apart: while one builds (and the tensor pipe works on its gradient) the other
+    // stages / drains -- in lockstep both builds share the pipe (20.7 K cycles of MMA per tile pair at ~72 per MMA) and
+    // both then wait on memory at the same time.  The second group starts building when the first has built its first tile.
+    if (X == 1) wait_bar(offset_bar, 0u);
+#endif
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 0);
       // ---- 16 band chunks: chunk r = halo row r; this lane's entries are Gx[(r - bpy, k - res)] at columns 4 wq + k
 #pragma unroll 1
       for (int r = 0; r < HY; ++r, ++cnt) {
@@ -271,26 +360,93 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(X, BAND_FULL, slot));
+        if ((tid & 127) == 0 && r == 3) BT_TRACE(ti, X * 12 + 1);
       }
-      // ---- the next tile's Gx while this tile's last MMAs run (every warp of the group is done reading the buffer)
-      named_bar_sync(bar_id, 128);
-      if (tile + (int)gridDim.x < a.total_tiles) stage_g(tile + gridDim.x);
-
-      // ---- drain: TMEM lane = position, column = channel
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 2);
+#ifndef CERB_BTC_NO_OFFSET
+      if (X == 0 && ti == 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(offset_bar);
+      }
+#endif
+      named_bar_sync(bar_id, 128);   // every warp of the group is done reading the Gx buffer
       int n, y0, x0;
       decode(tile, n, y0, x0);
       const int y = y0 + bpy, x = x0 + bpx;
       const bool pix_ok = y < g.H && x < g.W;
       const long long plane = (long long)g.H * g.W;
-      const uint32_t dcol = tlane + (uint32_t)(X * npad);
+      const uint32_t dcol = tlane + (uint32_t)(X * nacc * npad);
+      // 8 channels of this lane's position: the partial accumulators summed
+      auto ld_acc8 = [&](int c0, float* v) {
+        tmem_ld8(dcol + (uint32_t)c0, v);
+        for (int j = 1; j < nacc; ++j) {
+          float w[8];
+          tmem_ld8(dcol + (uint32_t)(j * npad + c0), w);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] += w[i];
+        }
+      };
+      const bool splat = X == 1 && a.flow != nullptr;
+      // ---- splat: sampling data of this position; do the tile's taps fit one shared-memory window?
+      float sx = 0.f, sy = 0.f, wx1 = 0.f, wx0 = 0.f, wy1 = 0.f, wy0 = 0.f;
+      bool inx = false, iny = false, bx1 = false, by1 = false, fits = false;
+      int ix0 = 0, iy0 = 0, box_ox = 0, box_oy = 0;
+      const int n_x2 = x2_item(g, n);
+      if (splat) {
+        const int yc = min(y, g.H - 1), xc = min(x, g.W - 1);
+        const float* fp = a.flow + (long long)n * g.fls[0] + (long long)yc * g.fls[2] + xc;
+        sx = sample_pos(xc, __ldg(fp), g.W, g.warp_mode, inx);
+        sy = sample_pos(yc, __ldg(fp + g.fls[1]), g.H, g.warp_mode, iny);
+        const float fx = floorf(sx), fy = floorf(sy);
+        ix0 = (int)fx; iy0 = (int)fy;
+        wx1 = fx + 1.f - sx; wx0 = sx - fx; wy1 = fy + 1.f - sy; wy0 = sy - fy;
+        bx1 = ix0 + 1 < g.W; by1 = iy0 + 1 < g.H;
+        if (a.use_box) {
+          int xmin = pix_ok ? ix0 : 0x7fffffff, xmax = pix_ok ? ix0 + 1 : -0x7fffffff;
+          int ymin = pix_ok ? iy0 : 0x7fffffff, ymax = pix_ok ? iy0 + 1 : -0x7fffffff;
+          xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+          ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
+          if (lane == 0) *reinterpret_cast<int4*>(bbox_red + 4 * wq) = make_int4(xmin, xmax, ymin, ymax);
+          named_bar_sync(bar_id, 128);
+          xmin = 0x7fffffff; xmax = -0x7fffffff; ymin = 0x7fffffff; ymax = -0x7fffffff;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int4 b = *reinterpret_cast<const int4*>(bbox_red + 4 * w);
+            xmin = min(xmin, b.x); xmax = max(xmax, b.y);
+            ymin = min(ymin, b.z); ymax = max(ymax, b.w);
+          }
+          box_ox = xmin & ~3;   // TMA box starts are 16-byte aligned
+          box_oy = ymin;
+          fits = xmin <= xmax && xmax - box_ox < BOX_W && ymax - box_oy < BOX_H;
+          if (fits && gt == 0) {   // x2 window of the first channel pass
+            mbar_arrive_expect_tx(xb_full, BOX_BYTES);
+            tma_load_4d(smem + OFF_BOX, &tm_x2, xb_full, box_ox, box_oy, 0, n_x2);
+          }
+          if (gt == 0 && a.path_ctr != nullptr) atomicAdd(&a.path_ctr[fits ? 1 : 2], 1ull);
+        }
+      }
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 3);
+      // ---- the next tile's Gx while this tile's last MMAs run
+      if (tile + (int)gridDim.x < a.total_tiles) stage_g(tile + gridDim.x);
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 4);
+
+      // ---- drain: TMEM lane = position, column = channel
       wait_bar(BAR(X, D_FULL, 0), (uint32_t)(ti & 1));
       tc_fence_after();
-      if (X == 0 || a.flow == nullptr) {
-        const int n_dst = X == 0 ? n : x2_item(g, n);
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 5);
+      auto release_d = [&]() {   // every TMEM read of this warp has landed: (with the other three) the next tile's MMAs may start
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(X, D_EMPTY, 0));
+      };
+      if (!splat) {
+        int n_dst = X == 0 ? n : n + a.g2_roll;
+        if (n_dst >= g.B) n_dst -= g.B;
         float* dst = (X == 0 ? a.gx1 : a.gsecond) + (long long)n_dst * g.C * plane + (long long)min(y, g.H - 1) * g.W + min(x, g.W - 1);
         for (int c0 = 0; c0 < npad; c0 += 8) {
           float v[8];
-          tmem_ld8(dcol + (uint32_t)c0, v);
+          ld_acc8(c0, v);
+          if (c0 + 8 >= npad) release_d();
           if (pix_ok) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -299,46 +455,119 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
         }
       } else {
         // gradient wrt the warped map -> through the bilinear taps of this position into grad_x2; flow gradient over channels
-        const int yc = min(y, g.H - 1), xc = min(x, g.W - 1);
-        const float* fp = a.flow + (long long)n * g.fls[0] + (long long)yc * g.fls[2] + xc;
-        bool inx, iny;
-        const float sx = sample_pos(xc, __ldg(fp), g.W, g.warp_mode, inx);
-        const float sy = sample_pos(yc, __ldg(fp + g.fls[1]), g.H, g.warp_mode, iny);
-        const Taps tp_in = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
-        const Taps tp_out = make_taps(sx, sy, g.H, g.W, g.W);
-        const float fx = floorf(sx), fy = floorf(sy);
-        const float wx1 = fx + 1.f - sx, wx0 = sx - fx, wy1 = fy + 1.f - sy, wy0 = sy - fy;
-        const bool bx1 = (int)fx + 1 < g.W, by1 = (int)fy + 1 < g.H;
-        const int n_x2 = x2_item(g, n);
-        const float* x2n = a.x2 + (long long)n_x2 * g.x2s[0];
-        float* gx2n = a.gx2 + (long long)n_x2 * g.C * plane;
+        const float w_nw = wx1 * wy1, w_ne = bx1 ? wx0 * wy1 : 0.f, w_sw = by1 ? wx1 * wy0 : 0.f, w_se = (bx1 && by1) ? wx0 * wy0 : 0.f;
         float gix = 0.f, giy = 0.f;
-        for (int c0 = 0; c0 < npad; c0 += 8) {
-          float v[8];
-          tmem_ld8(dcol + (uint32_t)c0, v);
-          if (pix_ok) {
-            float tv[8][4];
+        if (fits) {
+          // taps inside the window (byte offset within one channel plane of the box)
+          const uint32_t t_nw = (uint32_t)(((iy0 - box_oy) * BOX_W + (ix0 - box_ox)) * 4);
+          const uint32_t xbox = sbase + OFF_BOX;
+          // fixed-point scale of the tile: largest |gradient| over positions and channels (a first sweep over the accumulator)
+          float fs, ifs;
+          {
+            float am = 0.f;
+            for (int c0 = 0; c0 < npad; c0 += 8) {
+              float v[8];
+              ld_acc8(c0, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float* pch = x2n + (long long)min(c0 + i, g.C - 1) * g.x2s[1];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) tv[i][q] = __ldg(pch + tp_in.off[q]);
+              for (int i = 0; i < 8; ++i) am = fmaxf(am, fabsf(v[i]));
             }
+            const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(am * inv_c));   // non-negative floats order like integers
+            if (lane == 0) amax_red[wq] = wm;
+            named_bar_sync(bar_id, 128);
+            const uint32_t cm = max(max(amax_red[0], amax_red[1]), max(amax_red[2], amax_red[3]));
+            // cm < 2^(e+1) with e its exponent: scale 2^(22-e) keeps every term below 2^23 and a sum of 128 below 2^30
+            const int e = min(max((int)(cm >> 23) - 127, -100), 100);
+            fs = __uint_as_float((uint32_t)(127 + 22 - e) << 23);
+            ifs = __uint_as_float((uint32_t)(127 - 22 + e) << 23);
+          }
+          for (int c0 = 0; c0 < npad; c0 += CB) {
+            float v[8];
+            ld_acc8(c0, v);
+            if (c0 + CB >= npad) release_d();
+            // tap values of this pass's channels
+            wait_bar(xb_full, (uint32_t)(xcnt & 1));
+            ++xcnt;
+            float tv[CB][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (c0 + i < g.C) {
-                const float gv = v[i] * inv_c;
-                float* gp = gx2n + (long long)(c0 + i) * plane;
-                if (tp_out.w[0] != 0.f) red_add(gp + tp_out.off[0], gv * tp_out.w[0]);
-                if (tp_out.w[1] != 0.f) red_add(gp + tp_out.off[1], gv * tp_out.w[1]);
-                if (tp_out.w[2] != 0.f) red_add(gp + tp_out.off[2], gv * tp_out.w[2]);
-                if (tp_out.w[3] != 0.f) red_add(gp + tp_out.off[3], gv * tp_out.w[3]);
-                const float v_nw = tv[i][0];
-                const float v_ne = bx1 ? tv[i][1] : 0.f;
-                const float v_sw = by1 ? tv[i][2] : 0.f;
+            for (int i = 0; i < CB; ++i) {
+              const uint32_t pl = xbox + (uint32_t)(i * BOX_H * BOX_W * 4) + (pix_ok ? t_nw : 0u);
+              tv[i][0] = lds_f32(pl); tv[i][1] = lds_f32(pl + 4);
+              tv[i][2] = lds_f32(pl + BOX_W * 4); tv[i][3] = lds_f32(pl + BOX_W * 4 + 4);
+            }
+            // the gradient window of two passes ago has been read by its reduce; everyone is done with the x2 window
+            if (gt == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            named_bar_sync(bar_id, 128);
+            const uint32_t gbox = sbase + OFF_BOX + (uint32_t)(1 + (gcnt & 1)) * BOX_BYTES;
+            for (uint32_t o = (uint32_t)gt * 16u; o < BOX_BYTES; o += 128u * 16u) sts128(gbox + o, make_float4(0.f, 0.f, 0.f, 0.f));
+            if (gt == 0 && c0 + CB < npad) {
+              mbar_arrive_expect_tx(xb_full, BOX_BYTES);
+              tma_load_4d(smem + OFF_BOX, &tm_x2, xb_full, box_ox, box_oy, c0 + CB, n_x2);
+            }
+            named_bar_sync(bar_id, 128);
+            if (pix_ok) {
+#pragma unroll
+              for (int i = 0; i < CB; ++i) {
+                const float gv = (c0 + i < g.C) ? v[i] * inv_c : 0.f;
+                const float gs = gv * fs;
+                const uint32_t pl = gbox + (uint32_t)(i * BOX_H * BOX_W * 4) + t_nw;
+                red_shared_s32(pl, __float2int_rn(gs * w_nw));
+                red_shared_s32(pl + 4, __float2int_rn(gs * w_ne));
+                red_shared_s32(pl + BOX_W * 4, __float2int_rn(gs * w_sw));
+                red_shared_s32(pl + BOX_W * 4 + 4, __float2int_rn(gs * w_se));
+                const float v_nw = tv[i][0], v_ne = bx1 ? tv[i][1] : 0.f, v_sw = by1 ? tv[i][2] : 0.f;
                 const float v_se = (bx1 && by1) ? tv[i][3] : 0.f;
                 gix += gv * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
                 giy += gv * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
+              }
+            }
+            named_bar_sync(bar_id, 128);
+            // fixed point -> fp32 in place
+            for (uint32_t o = (uint32_t)gt * 16u; o < BOX_BYTES; o += 128u * 16u) {
+              const float4 q = lds128(gbox + o);
+              sts128(gbox + o, make_float4((float)__float_as_int(q.x) * ifs, (float)__float_as_int(q.y) * ifs,
+                                           (float)__float_as_int(q.z) * ifs, (float)__float_as_int(q.w) * ifs));
+            }
+            fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA's reads
+            named_bar_sync(bar_id, 128);
+            if (gt == 0) {
+              tma_reduce_add_4d(&tm_gx2, gbox, box_ox, box_oy, c0, n_x2);
+              tma_store_commit();
+            }
+            ++gcnt;
+          }
+        } else {
+          const Taps tp_in = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
+          const Taps tp_out = make_taps(sx, sy, g.H, g.W, g.W);
+          const float* x2n = a.x2 + (long long)n_x2 * g.x2s[0];
+          float* gx2n = a.gx2 + (long long)n_x2 * g.C * plane;
+          for (int c0 = 0; c0 < npad; c0 += 8) {
+            float v[8];
+            ld_acc8(c0, v);
+            if (c0 + 8 >= npad) release_d();
+            if (pix_ok) {
+              float tv[8][4];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float* pch = x2n + (long long)min(c0 + i, g.C - 1) * g.x2s[1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tv[i][q] = __ldg(pch + tp_in.off[q]);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (c0 + i < g.C) {
+                  const float gv = v[i] * inv_c;
+                  float* gp = gx2n + (long long)(c0 + i) * plane;
+                  if (tp_out.w[0] != 0.f) red_add(gp + tp_out.off[0], gv * tp_out.w[0]);
+                  if (tp_out.w[1] != 0.f) red_add(gp + tp_out.off[1], gv * tp_out.w[1]);
+                  if (tp_out.w[2] != 0.f) red_add(gp + tp_out.off[2], gv * tp_out.w[2]);
+                  if (tp_out.w[3] != 0.f) red_add(gp + tp_out.off[3], gv * tp_out.w[3]);
+                  const float v_nw = tv[i][0];
+                  const float v_ne = bx1 ? tv[i][1] : 0.f;
+                  const float v_sw = by1 ? tv[i][2] : 0.f;
+                  const float v_se = (bx1 && by1) ? tv[i][3] : 0.f;
+                  gix += gv * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
+                  giy += gv * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
+                }
               }
             }
           }
@@ -349,94 +578,149 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
           gf[plane] = iny ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(X, D_EMPTY, 0));
+      if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 6);
       // the staged Gx of the next tile is complete in every warp of the group before anyone builds from it
       named_bar_sync(bar_id, 128);
     }
-  } else if (warp < MMA_WARP) {
+    if (X == 1 && gt == 0) tma_store_wait_all0();   // the last gradient windows have been added to grad_x2
+  } else if (warp < TMA_WARP) {
     // =========================== operand split: hi = tf32(v) in place, lo = v - hi ===========================
-    const int st = tid - 2 * GROUP_WARPS * 32;
+    // One WARP per operand tile (split warp sw takes gradient sw % 2, every (SPLIT_WARPS / 2)-th row): the tiles of a row pair
+    // are split concurrently -- with all warps on one tile the chain wait -> 3 loads -> stores -> fence -> arrive of a
+    // single tile (~600 cycles) was the period of the whole operand pipeline (clock64 trace).
+    const int sw = warp - 2 * GROUP_WARPS;
+    const int X = sw & 1, rstep = SPLIT_WARPS / 2, r0 = sw >> 1;
     const int units = npad * (KU / 4);   // 16-byte chunks that the MMAs read (columns 0..23 of every channel row)
     int cnt = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
       for (int r = 0; r < HY; ++r, ++cnt) {
+        if ((r % rstep) != r0) continue;
         const int stg = cnt % nstg, use = cnt / nstg;
+        const uint32_t hi_t = sbase + (uint32_t)((X * nstg + stg) * 2) * STG;
+        wait_bar(BAR(X, RAW_FULL, stg), (uint32_t)(use & 1));
+        if (lane == 0 && (r == 0 || r == 15)) BT_TRACE(cnt / HY, 36 + X + (r == 15 ? 2 : 0));
+        for (int u0 = lane; u0 < units; u0 += 4 * 32) {   // four independent loads in flight
+          uint32_t ad[4];
+          float4 v[4];
 #pragma unroll
-        for (int X = 0; X < 2; ++X) {
-          const uint32_t hi_t = sbase + (uint32_t)((X * nstg + stg) * 2) * STG;
-          wait_bar(BAR(X, RAW_FULL, stg), (uint32_t)(use & 1));
-          for (int u = st; u < units; u += SPLIT_WARPS * 32) {
+          for (int k = 0; k < 4; ++k) {
+            const int u = min(u0 + 32 * k, units - 1);
             const int row = u / (KU / 4), c = u - row * (KU / 4);
-            const uint32_t ad = hi_t + (uint32_t)row * 128u + ((uint32_t)(c ^ (row & 7)) << 4);
-            const float4 v = lds128(ad);
-            float4 h, l;
-            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-            sts128(ad, h);
-            sts128(ad + STG, l);
+            ad[k] = hi_t + (uint32_t)row * 128u + ((uint32_t)(c ^ (row & 7)) << 4);
+            v[k] = lds128(ad[k]);
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(X, S_FULL, stg));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (u0 + 32 * k < units) {
+              float4 h, l;
+              split_tf32(v[k].x, h.x, l.x); split_tf32(v[k].y, h.y, l.y); split_tf32(v[k].z, h.z, l.z); split_tf32(v[k].w, h.w, l.w);
+              sts128(ad[k], h);
+              sts128(ad[k] + STG, l);
+            }
+          }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(X, S_FULL, stg));
       }
     }
-  } else if (warp == MMA_WARP) {
-    // =========================== MMA issue: one lane ===========================
-    if (lane == 0) {
+  } else if (warp >= MMA_WARP) {
+    // =========================== MMA issue: one lane of up to three warps per gradient ===========================
+    // A tcgen05.mma of N <= 128 costs the issuing thread ~140 cycles (clock64 trace, elimination builds: the same for N = 16
+    // and N = 48, halved by a second issuing warp), several times what the tensor pipe needs for it.  Warp (X, j) issues the
+    // products of the 3xTF32 split that accumulate into partial accumulator j of gradient X -- hi*hi, lo*hi, hi*lo with
+    // three accumulators -- and commits onto the shared barriers (counts = nacc).
+    // (16 warps in all: two issuing warps per gradient -- one for hi*hi, one for both cross terms)
+    const int mw = warp - MMA_WARP, X = mw >> 1, jw = mw & 1;
+    // accumulators this warp issues into
+    const uint32_t accmask = nacc == 3 ? (jw == 0 ? 1u : 6u) : (jw < nacc ? 1u << jw : 0u);
+    if (lane == 0 && accmask != 0u) {
       // instruction descriptor: D fp32 (bit 4), A / B tf32 (2 at bits 7-9 / 10-12), K-major, N = npad, M = 128
+#ifdef CERB_BTC_X_N16
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+#else
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-      int cnt = 0, ti = 0;
+#endif
+      // which products this warp issues, and whether a product is the first to write the accumulator in a tile
+      uint32_t d_col[3], first_acc[3];
+      bool mine[3];
+#pragma unroll
+      for (int prod = 0; prod < 3; ++prod) {
+        const int j = nacc == 1 ? 0 : (prod < nacc ? prod : prod - nacc);
+        mine[prod] = ((accmask >> j) & 1u) != 0u;
+        d_col[prod] = tmem + (uint32_t)((X * nacc + j) * npad);
+        first_acc[prod] = prod < nacc ? 0u : 1u;
+      }
+      int stg = 0, slot = 0;
+      uint32_t sphase = 0, bphase = 0;   // phase parities of the operand-stage / band-slot rings
+      int ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
-        for (int r = 0; r < HY; ++r, ++cnt) {
-          const int stg = cnt % nstg, suse = cnt / nstg;
-          const int slot = cnt % nslot, buse = cnt / nslot;
+        wait_bar(BAR(X, D_EMPTY, 0), (uint32_t)((ti & 1) ^ 1));   // the previous tile's accumulators have been drained
+        for (int r = 0; r < HY; ++r) {
+          wait_bar(BAR(X, S_FULL, stg), sphase);
+          wait_bar(BAR(X, BAND_FULL, slot), bphase);
+          tc_fence_after();
+          if (jw == 0 && r == 0) BT_TRACE(ti, 24 + X);
+          if (jw == 0 && r == 8) BT_TRACE(ti, 26 + X);
+          if (jw == 0 && r == 15) BT_TRACE(ti, 28 + X);
+          const uint32_t a_hi = tmem + RING0 + (uint32_t)((X * nslot + slot) * SLOT_COLS);
+          const uint64_t b_hi = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2) * STG);
+          const uint64_t b_lo = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2 + 1) * STG);
 #pragma unroll
-          for (int X = 0; X < 2; ++X) {
-            if (r == 0) {   // the previous tile's accumulator of this gradient has been drained
-              wait_bar(BAR(X, D_EMPTY, 0), (uint32_t)((ti & 1) ^ 1));
-            }
-            wait_bar(BAR(X, S_FULL, stg), (uint32_t)(suse & 1));
-            wait_bar(BAR(X, BAND_FULL, slot), (uint32_t)(buse & 1));
-            tc_fence_after();
-            const uint32_t d_t = tmem + (uint32_t)(X * npad);
-            const uint32_t a_hi = tmem + RING0 + (uint32_t)((X * nslot + slot) * SLOT_COLS), a_lo = a_hi + KU;
-            const uint64_t b_hi = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2) * STG);
-            const uint64_t b_lo = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2 + 1) * STG);
+          for (int ks = 0; ks < KU / 8; ++ks) {
+            const uint64_t ko = (uint64_t)(2 * ks);   // 32 bytes per K step inside the 128-byte swizzle atom
 #pragma unroll
-            for (int ks = 0; ks < KU / 8; ++ks) {
-              const uint64_t ko = (uint64_t)(2 * ks);   // 32 bytes per K step inside the 128-byte swizzle atom
-              umma_tf32_ta(d_t, a_hi + 8u * ks, b_hi + ko, idesc, (r > 0 || ks > 0) ? 1u : 0u);
-              umma_tf32_ta(d_t, a_lo + 8u * ks, b_hi + ko, idesc, 1u);
-              umma_tf32_ta(d_t, a_hi + 8u * ks, b_lo + ko, idesc, 1u);
+            for (int prod = 0; prod < 3; ++prod) {
+              const uint32_t acc = (r > 0 || ks > 0) ? 1u : first_acc[prod];
+              const uint32_t a_t = (prod == 1 ? a_hi + KU : a_hi) + 8u * ks;     // hi*hi, lo*hi, hi*lo
+#if defined(CERB_BTC_X_NOMMA)   // CERB_BTC_X_*: timing-only elimination builds (tools/ab_variants.py), results are wrong
+              (void)acc; (void)a_t;
+#else
+              if (mine[prod]) umma_tf32_ta(d_col[prod], a_t, (prod == 2 ? b_lo : b_hi) + ko, idesc, acc);
+#endif
             }
-            umma_commit(BAR(X, BAND_EMPTY, slot));
-            umma_commit(BAR(X, S_EMPTY, stg));
-            if (r == HY - 1) umma_commit(BAR(X, D_FULL, 0));
           }
+          umma_commit(BAR(X, BAND_EMPTY, slot));
+          umma_commit(BAR(X, S_EMPTY, stg));
+          if (r == HY - 1) umma_commit(BAR(X, D_FULL, 0));
+          if (jw == 0 && r == HY - 1) BT_TRACE(ti, 30 + X);
+          if (++stg == nstg) { stg = 0; sphase ^= 1u; }
+          if (++slot == nslot) { slot = 0; bphase ^= 1u; }
         }
       }
     }
     __syncwarp();
-  } else {
-    // =========================== TMA issue: one lane ===========================
+  } else if (warp < MMA_WARP) {
+    // =========================== TMA issue: one lane of one warp per gradient ===========================
     if (lane == 0) {
+      const int X = warp - TMA_WARP;
+      const CUtensorMap* tm = X == 0 ? &tm_s0 : &tm_s1;
+      const int roll = X == 0 ? a.s0_roll : 0;
       int cnt = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         int n, y0, x0;
         decode(tile, n, y0, x0);
-        int n0 = n + a.s0_roll;
+        int n0 = n + roll;
         if (n0 >= g.B) n0 -= g.B;
+        // the next tile's inputs into L2 while this one is processed: its grad_out / out planes (incl. the 4-pixel halo the
+        // second gradient reads) and its operand rows
+        if (tile + (int)gridDim.x < a.total_tiles) {
+          int nn, ny0, nx0;
+          decode(tile + gridDim.x, nn, ny0, nx0);
+          int nn0 = nn + roll;
+          if (nn0 >= g.B) nn0 -= g.B;
+          if (a.use_pf && X == 0) {
+            tma_prefetch_4d(&tm_go, nx0 - MD, ny0 - MD, 0, nn);
+            if (g.has_act && a.out != nullptr) tma_prefetch_4d(&tm_o, nx0 - MD, ny0 - MD, 0, nn);
+          }
+          for (int r = 0; r < HY; ++r) tma_prefetch_4d(tm, nx0 - MD, ny0 - MD + r, 0, nn0);
+        }
         for (int r = 0; r < HY; ++r, ++cnt) {
           const int stg = cnt % nstg, use = cnt / nstg;
-#pragma unroll
-          for (int X = 0; X < 2; ++X) {
-            wait_bar(BAR(X, S_EMPTY, stg), (uint32_t)((use & 1) ^ 1));
-            mbar_arrive_expect_tx(BAR(X, RAW_FULL, stg), STG);
-            tma_load_4d(smem + (uint32_t)((X * nstg + stg) * 2) * STG, X == 0 ? &tm_s0 : &tm_s1, BAR(X, RAW_FULL, stg), x0 - MD,
-                        y0 - MD + r, 0, X == 0 ? n0 : n);
-          }
+          wait_bar(BAR(X, S_EMPTY, stg), (uint32_t)((use & 1) ^ 1));
+          if (r == 0 || r == 15) BT_TRACE(cnt / HY, 32 + X + (r == 15 ? 2 : 0));
+          mbar_arrive_expect_tx(BAR(X, RAW_FULL, stg), STG);
+          tma_load_4d(smem + (uint32_t)((X * nstg + stg) * 2) * STG, tm, BAR(X, RAW_FULL, stg), x0 - MD, y0 - MD + r, 0, n0);
         }
       }
     }
@@ -444,6 +728,9 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
   }
   tc_fence_before();
   __syncthreads();
+#ifdef CERB_BTC_TRACE
+  if (tid == 0 && a.dbg) a.dbg[(long long)blockIdx.x * 192 + 191] = clock64();
+#endif
   if (warp == MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -456,6 +743,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
 bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long long s0s[3], const void* x1) {
   if (dtype != CERB_F32 || g.k != 1 || g.s1 != 1 || g.s2 != 1 || g.md != btc::MD || g.pad != g.md) return false;
   if (g.C > 128 || g.C < 1 || g.outH != g.H || g.outW != g.W) return false;
+  if (81 * g.os[1] + (long long)g.H * g.os[2] >= (1ll << 31)) return false;   // 32-bit offsets inside one item of grad_out
   if (((uintptr_t)s0 & 15) || ((uintptr_t)x1 & 15)) return false;
   for (int i = 0; i < 3; ++i)
     if ((s0s[i] * 4) % 16 != 0 || (g.x1s[i] * 4) % 16 != 0) return false;
@@ -464,7 +752,7 @@ bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long 
 
 cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long long s0s[3], int s0_roll, const void* x1,
                                     const void* x2, const float* flow, const void* out, const void* gout, void* gx1,
-                                    void* gsecond, void* gx2_splat, float* gflow, cudaStream_t stream) {
+                                    void* gsecond, int gsecond_roll, void* gx2_splat, float* gflow, cudaStream_t stream) {
   btc::Args a;
   a.g = g;
   a.gout = (const float*)gout; a.out = (const float*)out;
@@ -475,21 +763,54 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
   a.total_tiles = g.B * a.tiles_x * a.tiles_y;
   a.npad = (g.C + 15) / 16 * 16;
   a.s0_roll = s0_roll;
-  // TMEM: 2 accumulators of npad columns + 2 band rings of nslot x 48; shared memory: 2 x nstg stages of (hi, lo) tiles
-  a.nslot = (512 - 2 * a.npad) / (2 * btc::SLOT_COLS);
+  a.g2_roll = gsecond_roll;
+  // TMEM (512 columns): 2 x nacc accumulators of npad columns + 2 band rings of nslot x 48; as many partial accumulators
+  // as leave two band slots per gradient
+  static const int force_nacc = getenv("CERB_DEBUG_BWD_TC_NACC") ? atoi(getenv("CERB_DEBUG_BWD_TC_NACC")) : 0;
+  a.nacc = 3;
+  while (a.nacc > 1 && (512 - 2 * a.nacc * a.npad) / (2 * btc::SLOT_COLS) < 2) --a.nacc;
+  if (force_nacc >= 1 && force_nacc < a.nacc) a.nacc = force_nacc;
+  a.nslot = (512 - 2 * a.nacc * a.npad) / (2 * btc::SLOT_COLS);
   if (a.nslot > btc::MAXSLOT) a.nslot = btc::MAXSLOT;
-  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::NBARS * 8 + 16 + 1024;
-  const size_t stage = 2 * (size_t)a.npad * 128;
-  a.nstg = (int)((227 * 1024 - fixed) / (2 * stage));
-  if (a.nstg > btc::MAXSTG) a.nstg = btc::MAXSTG;
-  if (a.nslot < 2 || a.nstg < 2) return cudaErrorNotSupported;
-  const size_t smem = 2 * (size_t)a.nstg * stage + fixed;
-  CUtensorMap tm0, tm1;
+  a.path_ctr = get_path_counters();
+  a.dbg = get_trace_buffer();
+  CUtensorMap tm0, tm1, tmx, tmg;
   memset(&tm0, 0, sizeof(tm0));
   memset(&tm1, 0, sizeof(tm1));
+  memset(&tmx, 0, sizeof(tmx));
+  memset(&tmg, 0, sizeof(tmg));
   if (!make_tmap_nchw(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s0, g.W, g.H, g.C, g.B, s0s, btc::KBOX, 1, a.npad, true) ||
       !make_tmap_nchw(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x1, g.W, g.H, g.C, g.B, g.x1s, btc::KBOX, 1, a.npad, true))
     return cudaErrorNotSupported;
+  // splat through shared-memory windows: x2 (tap values) and grad_x2 (contiguous) as TMA tensors, three windows of shared memory
+  a.use_box = 0;
+  // (off by default: the three windows leave room for only two operand stages per gradient, and the operand pipeline --
+  // commit -> TMA -> split -> MMA, ~4 K cycles per round trip in the clock64 trace -- then bounds the tile; the launcher
+  // runs the splat as its own kernel instead.  CERB_DEBUG_BWD_TC_BOX=1 turns the fused form on.)
+  static const bool no_box = getenv("CERB_DEBUG_BWD_TC_BOX") == nullptr;
+  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::NBARS * 8 + 24 + 64 + 16 + 1024;
+  const size_t stage = 2 * (size_t)a.npad * 128;
+  if (flow != nullptr && !no_box) {
+    const long long gs[3] = {(long long)g.C * g.H * g.W, (long long)g.H * g.W, (long long)g.W};
+    const size_t need = fixed + 3 * (size_t)btc::BOX_BYTES + 2 * 2 * stage;   // at least two operand stages per gradient
+    if (need <= 227 * 1024 &&
+        make_tmap_nchw(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, btc::BOX_W, btc::BOX_H, btc::CB, false) &&
+        make_tmap_nchw(&tmg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gx2_splat, g.W, g.H, g.C, g.B, gs, btc::BOX_W, btc::BOX_H, btc::CB, false))
+      a.use_box = 1;
+  }
+  CUtensorMap tmgo, tmo;
+  memset(&tmgo, 0, sizeof(tmgo));
+  memset(&tmo, 0, sizeof(tmo));
+  static const bool no_pf = getenv("CERB_DEBUG_BWD_TC_NOPF") != nullptr;
+  a.use_pf = !no_pf &&
+             make_tmap_nchw(&tmgo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gout, g.outW, g.outH, g.D2, g.B, g.os, btc::KU, btc::HY, g.D2, false) &&
+             (out == nullptr ||
+              make_tmap_nchw(&tmo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, g.outW, g.outH, g.D2, g.B, g.os, btc::KU, btc::HY, g.D2, false));
+  const size_t boxes = a.use_box ? 3 * (size_t)btc::BOX_BYTES : 0;
+  a.nstg = (int)((227 * 1024 - fixed - boxes) / (2 * stage));
+  if (a.nstg > btc::MAXSTG) a.nstg = btc::MAXSTG;
+  if (a.nslot < 2 || a.nstg < 2) return cudaErrorNotSupported;
+  const size_t smem = 2 * (size_t)a.nstg * stage + boxes + fixed;
   auto kern = btc::corr_bwd_tc_kernel;
   static unsigned long long attr_devs = 0ull;   // function attributes are per device
   {
@@ -504,7 +825,7 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
   }
   int grid = num_sms_current();
   if (grid > a.total_tiles) grid = a.total_tiles;
-  kern<<<grid, btc::NTHREADS, smem, stream>>>(a, tm0, tm1);
+  kern<<<grid, btc::NTHREADS, smem, stream>>>(a, tm0, tm1, tmx, tmg, tmgo, tmo);
   return cudaGetLastError();
 }
 

@@ -57,6 +57,7 @@ cudaError_t launch_photometric_forward(const float* orig, const float* src, cons
 cudaError_t launch_photometric_backward(const float* orig, const float* src, const float* flow, const float* gloss, float* gflow,
                                         int B, int C, int H, int W, float l1_w, float ssim_w, int mode, cudaStream_t stream);
 
+void set_backward_kernel_mode(int mode);   // -1 automatic, 0 CUDA-core kernels, 1 tensor-core kernel wherever supported
 void count_launches(int n);
 void set_trace_buffer(long long* p);
 void set_trace_iter(int it);
