@@ -602,7 +602,8 @@ def main_gpu(args, rank, world, local_rank):
     }
 
     # ---- backward of the fused level op: dominant level of this workload and the HRNet training shape
-    def time_backward(C, H, W, B, roll):
+    def time_backward(C, H, W, B, roll, kernel=-1):
+        lib.cerb_debug_set_backward_kernel(kernel)   # -1 automatic (what the product runs), 1 tensor-core kernel + window splat
         nset = max(2, int(300e6 // level_bytes_bwd(C, H, W, True, B)) + 1)
         bs = []
         for s in range(nset):
@@ -628,6 +629,7 @@ def main_gpu(args, rank, world, local_rank):
             b.record(stream)
         torch.cuda.synchronize()
         us = a.elapsed_time(b) * 1e3 / (reps * nset)
+        lib.cerb_debug_set_backward_kernel(-1)
         byts = level_bytes_bwd(C, H, W, True, B)
         fl_ = 2 * level_flops(C, H, W, B)
         return {"C": C, "H": H, "W": W, "batch": B, "us_per_call": round(us, 2), "kernels_per_call": int(kern),
@@ -638,9 +640,46 @@ def main_gpu(args, rank, world, local_rank):
     Cd, Hd, Wd = dom["C"], dom["H"], dom["W"]
     bwd_dom = time_backward(Cd, Hd, Wd, DIRS, DIRS // 2)
     bwd_train = time_backward(*HRNET_TRAIN_LEVEL[:3], HRNET_TRAIN_LEVEL[3], 0)
+    # the tensor-core backward (costvolume_bwd_tc.cu, opt-in: cerb_debug_set_backward_kernel(1)) on the same shapes
+    bwd_tc = {"dominant_level": time_backward(Cd, Hd, Wd, DIRS, DIRS // 2, kernel=1),
+              "hrnet_train_level_b8": time_backward(*HRNET_TRAIN_LEVEL[:3], HRNET_TRAIN_LEVEL[3], 0, kernel=1),
+              "note": "tcgen05 banded GEMMs (3xTF32) + shared-memory-window splat kernel; parity-tested, not the default"}
+
+    # stand-alone flow_warp backward (cerb_flow_warp_backward: shared-memory-window splat, costvolume_splat.cu)
+    def time_flow_warp_backward(C, H, W, B):
+        sets_ = []
+        for s_ in range(4):
+            g = torch.Generator(device=dev).manual_seed(99 + s_)
+            img = torch.randn(B, C, H, W, device=dev, generator=g)
+            fl = (torch.randn(B, 2, H, W, device=dev, generator=g) * 1.5).clamp_(-6, 6)
+            sets_.append((img, fl, torch.randn(B, C, H, W, device=dev, generator=g)))
+        ctr = torch.zeros(4, dtype=torch.int64, device=dev)
+        lib.cerb_debug_set_path_counters(ctypes.c_void_p(ctr.data_ptr()))
+        with torch.cuda.stream(stream):
+            for t in sets_:
+                ops.flow_warp_backward(*t)
+            torch.cuda.synchronize()
+            lib.cerb_debug_set_path_counters(None)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record(stream)
+            for _ in range(reps):
+                for t in sets_:
+                    ops.flow_warp_backward(*t)
+            b.record(stream)
+        torch.cuda.synchronize()
+        us = a.elapsed_time(b) * 1e3 / (reps * len(sets_))
+        byts = B * C * H * W * 4 * 3 + B * H * W * 16
+        c_ = ctr.cpu().tolist()
+        return {"C": C, "H": H, "W": W, "batch": B, "us_per_call": round(us, 2), "launches": "memset + window-splat kernel",
+                "algorithmic_MB": round(byts / 1e6, 3), "GBps": round(byts / us / 1e3, 1), "hbm_frac": round(byts / us / 1e3 / hbm_peak, 4),
+                "window_tiles": int(c_[1]), "scattered_atomics_tiles": int(c_[2]),
+                "scattered_atomics_kernel_us_r02_microbench": 207.9}
+    fwb = time_flow_warp_backward(*HRNET_TRAIN_LEVEL[:3], HRNET_TRAIN_LEVEL[3])
     roofline_bwd = {"bound": "hbm", "achieved": bwd_dom["GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": bwd_dom["frac"],
                     "traffic": None, "algorithmic_bytes_formula": "B*H*W*4*(2*81 + 4C + 4) (SURVEY 8d)",
-                    "dominant_level": bwd_dom, "hrnet_train_level_b8": bwd_train,
+                    "dominant_level": bwd_dom, "hrnet_train_level_b8": bwd_train, "tensor_core_path": bwd_tc,
+                    "flow_warp_backward_hrnet_b8": fwb,
                     "method": "CUDA events around back-to-back cerb_warp_corr_backward calls over rotating buffer sets (stream launches)"}
 
     # ---- end to end with HOST buffers (pinned): every step copies its inputs host->device and its

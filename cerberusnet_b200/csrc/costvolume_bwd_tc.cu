@@ -82,6 +82,7 @@ struct Args {
   int tiles_x, tiles_y, total_tiles;
   int npad, nstg, nslot;  // N of the MMA, operand stages per gradient, band slots per gradient
   int nacc;               // partial accumulators per gradient (1..3)
+  int no_cat;             // debugging: three separate MMAs per K step even with three accumulators
   int g2_roll;            // no flow: batch roll applied when writing gsecond (x2_batch_roll when it is grad_x2 itself)
   int s0_roll;            // batch roll applied to the TMA item coordinate of the first gradient's S (x2 itself when no flow)
   int use_pf;             // tensor maps tm_go / tm_o valid: the next tile's grad_out / out planes are prefetched into L2
@@ -641,6 +642,8 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
 #else
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 #endif
+      const uint32_t idesc_cat = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * npad) >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+      const bool cat = nacc == 3 && !a.no_cat;
       // which products this warp issues, and whether a product is the first to write the accumulator in a tile
       uint32_t d_col[3], first_acc[3];
       bool mine[3];
@@ -666,6 +669,21 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
           const uint32_t a_hi = tmem + RING0 + (uint32_t)((X * nslot + slot) * SLOT_COLS);
           const uint64_t b_hi = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2) * STG);
           const uint64_t b_lo = make_desc(sbase + (uint32_t)((X * nstg + stg) * 2 + 1) * STG);
+          if (cat) {
+            // Three partial accumulators per gradient, laid out [hi*hi | hi*lo | lo*hi]: the two products that share the band's
+            // hi part are ONE MMA of N = 2 npad -- the hi and lo operand tiles of a stage are adjacent in shared memory, so one
+            // descriptor covers both -- and an MMA costs the tensor pipe about the same ~72 cycles for any N <= 128 here
+            // (elimination builds: N = 16 and N = 48 take the same time).  Two MMAs per K step instead of three.
+#if !defined(CERB_BTC_X_NOMMA)
+#pragma unroll
+            for (int ks = 0; ks < KU / 8; ++ks) {
+              const uint64_t ko = (uint64_t)(2 * ks);
+              const uint32_t acc = (r > 0 || ks > 0) ? 1u : 0u;
+              if (jw == 0) umma_tf32_ta(tmem + (uint32_t)(X * 3 * npad), a_hi + 8u * ks, b_hi + ko, idesc_cat, acc);
+              else umma_tf32_ta(tmem + (uint32_t)((X * 3 + 2) * npad), a_hi + KU + 8u * ks, b_hi + ko, idesc, acc);
+            }
+#endif
+          } else
 #pragma unroll
           for (int ks = 0; ks < KU / 8; ++ks) {
             const uint64_t ko = (uint64_t)(2 * ks);   // 32 bytes per K step inside the 128-byte swizzle atom
@@ -772,6 +790,8 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
   if (force_nacc >= 1 && force_nacc < a.nacc) a.nacc = force_nacc;
   a.nslot = (512 - 2 * a.nacc * a.npad) / (2 * btc::SLOT_COLS);
   if (a.nslot > btc::MAXSLOT) a.nslot = btc::MAXSLOT;
+  static const bool no_cat = getenv("CERB_DEBUG_BWD_TC_NOCAT") != nullptr;
+  a.no_cat = no_cat ? 1 : 0;
   a.path_ctr = get_path_counters();
   a.dbg = get_trace_buffer();
   CUtensorMap tm0, tm1, tmx, tmg;

@@ -15,6 +15,11 @@ ncu --set full --clock-control none --import-source on -k regex:warp_corr_fwd -s
 # (3) full capture of the fused backward kernel (HRNet training level, batch 8)
 ncu --set full --clock-control none --import-source on -k regex:corr_bwd_fused -s 1 -c 1 \
     -o gpurun_out/prof_bwd_${TAG} python tools/profile_backward.py > gpurun_out/ncu_bwd_${TAG}.log 2>&1
+# (3b) full captures of the tensor-core backward kernel and of the shared-memory-window splat kernel (same shape)
+ncu --set full --clock-control none --import-source on -k regex:corr_bwd_tc -s 1 -c 1 \
+    -o gpurun_out/prof_bwd_tc_${TAG} python tools/profile_backward_tc.py > gpurun_out/ncu_bwd_tc_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:flow_warp_bwd_box -s 1 -c 1 \
+    -o gpurun_out/prof_splat_${TAG} python tools/profile_backward_tc.py > gpurun_out/ncu_splat_${TAG}.log 2>&1
 # (4) compute-sanitizer over cases that touch every kernel path
 for tool in memcheck synccheck; do
   timeout 420 compute-sanitizer --tool $tool python tools/sanitize_cases.py > gpurun_out/sanitizer_${tool}_${TAG}.txt 2>&1

@@ -13,3 +13,8 @@ x = torch.randn(2, 16, 32, 64, device=dev); fl = torch.randn(2, 2, 32, 64, devic
 out = ops.warp_corr_forward(x, x, fl, 4, 1, 4, 1, 1, 1, 0, 0.1, variant=7)
 ops.warp_corr_backward(x, x, fl, out, torch.randn_like(out), 4, 1, 4, 1, 1, 1, 0, 0.1)
 torch.cuda.synchronize(); print("done")
+# tensor-core backward + window splat (shared-memory reductions, TMA reduce)
+cb.lib().cerb_debug_set_backward_kernel(1)
+ops.warp_corr_backward(x, x, fl, out, torch.randn_like(out), 4, 1, 4, 1, 1, 1, 0, 0.1)
+cb.lib().cerb_debug_set_backward_kernel(-1)
+torch.cuda.synchronize(); print("done")

@@ -60,4 +60,16 @@ torch.cuda.synchronize()
 x = torch.randn(1, 6, 12, 20, device=dev); f = torch.randn(1, 2, 12, 20, device=dev) * 3
 o = ops.flow_warp_forward(x, f); ops.flow_warp_backward(x, f, torch.randn_like(o))
 ops.warp_corr_forward(x, x, f, 3, 3, 4, 2, 2); torch.cuda.synchronize()
+# tensor-core backward (banded GEMMs in TMEM) + shared-memory-window splat: windows that fit, a wild flow (scattered atomics),
+# ragged tiles, C = 64 / 96 (two / one partial accumulators), no flow, the stand-alone flow_warp backward through the windows
+cb.lib().cerb_debug_set_backward_kernel(1)
+run(2, 16, 24, 64, True)
+run(1, 48, 40, 96, True, sigma=1.5)
+run(3, 20, 17, 36, True)
+run(1, 32, 16, 48, True, sigma=14.0)
+run(1, 64, 16, 32, True)
+run(1, 96, 16, 32, False)
+cb.lib().cerb_debug_set_backward_kernel(-1)
+x = torch.randn(2, 12, 24, 48, device=dev); f = torch.randn(2, 2, 24, 48, device=dev) * 2
+ops.flow_warp_backward(x, f, torch.randn_like(x)); torch.cuda.synchronize()
 print("sanitize cases done")

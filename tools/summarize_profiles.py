@@ -83,6 +83,34 @@ try:
     open(f"profiles/{rnd}_ncu_backward_fused.txt", "w").write("\n".join(ob) + "\n")
 except Exception as exc:  # noqa: BLE001
     print("no backward capture:", exc)
+# ---- tensor-core backward kernel and window-splat kernel
+for rep, dst, head in (
+        (f"gpurun_out/prof_bwd_tc_{tag}.ncu-rep", f"profiles/{rnd}_ncu_backward_tc.txt",
+         ["# ncu --set full --clock-control none --import-source on -k regex:corr_bwd_tc -s 1 -c 1  python tools/profile_backward_tc.py",
+          "# kernel: cerb::btc::corr_bwd_tc_kernel (HRNet training level: B=8, C=48, 128x256; both correlation gradients as banded GEMMs,",
+          "#         2048 tiles of 8x16 on 148 persistent CTAs of 512 threads; opt-in path: cerb_debug_set_backward_kernel(1))", ""]),
+        (f"gpurun_out/prof_splat_{tag}.ncu-rep", f"profiles/{rnd}_ncu_splat_window.txt",
+         ["# ncu --set full --clock-control none --import-source on -k regex:flow_warp_bwd_box -s 1 -c 1  python tools/profile_backward_tc.py",
+          "# kernel: cerb::splat::flow_warp_bwd_box_kernel (B=8, C=48, 128x256: 2048 CTAs of 128 threads, 4 per SM; x2 window in by TMA,",
+          "#         fixed-point ATOMS into the gradient window, one UTMAREDG per 8 channels)", ""])):
+    try:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        ob = list(head)
+        for w in want:
+            if w in hdr:
+                i = hdr.index(w)
+                ob.append(f"{w} [{units[i]}]: {', '.join(r[i] for r in data)}")
+        ob += ["", "warp stall reasons (issue-stalled warps per issue-active cycle):"]
+        for i, h in enumerate(hdr):
+            if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
+                v = float(data[0][i])
+                if v >= 0.05:
+                    ob.append(f"  {h.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', '')}: {v:.2f}")
+        open(dst, "w").write("\n".join(ob) + "\n")
+    except Exception as exc:  # noqa: BLE001
+        print("no capture", rep, exc)
 # ---- sanitizer logs (memcheck / synccheck verbatim, racecheck: one line per distinct hazard site + the summary)
 for tool in ("memcheck", "synccheck"):
     src = f"gpurun_out/sanitizer_{tool}_{tag}.txt"
