@@ -1,7 +1,9 @@
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch, torch.nn.functional as F
+import cerberusnet_b200 as cb
 from cerberusnet_b200 import ops
+cb.lib().cerb_debug_set_backward_kernel(0)   # the fused CUDA-core kernel (AUTO takes the tensor-core kernel at this shape)
 B, C, H, W = 8, 48, 128, 256
 dev = torch.device("cuda:0")
 x1 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1); x2 = F.leaky_relu(torch.randn(B, C, H, W, device=dev), 0.1)
