@@ -123,22 +123,33 @@ flow_warp_bwd_box_kernel(const Args a, const __grid_constant__ CUtensorMap tm_im
     if (tid == 0) {
       mbar_arrive_expect_tx(&xb_full, BOX_BYTES);
       tma_load_4d(smem, &tm_img, &xb_full, box_ox, box_oy, 0, n2);
+      // (prefetching the later passes' windows into L2 here with cp.async.bulk.prefetch.tensor made the kernel 5-15 % slower)
     }
     const uint32_t t_nw = (uint32_t)(((iy0 - box_oy) * BOX_W + (ix0 - box_ox)) * 4);
+    // the gradients of a pass are requested one pass ahead: a first-touch load from HBM takes several thousand cycles here,
+    // and with one request per pass that latency, not the shared-memory work, was the period of a pass
+    float gn[CB];
+#pragma unroll
+    for (int i = 0; i < CB; ++i) gn[i] = __ldg(gop + (long long)min(i, a.C - 1) * plane);
     for (int c0 = 0, ps = 0; c0 < a.C; c0 += CB, ++ps) {
       // this pass's gradients; fixed-point scale from the largest of the tile
       float gv[CB];
       float am = 0.f;
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
-        const float v = __ldg(gop + (long long)min(c0 + i, a.C - 1) * plane);
-        gv[i] = (pix_ok && c0 + i < a.C) ? v : 0.f;
+        gv[i] = (pix_ok && c0 + i < a.C) ? gn[i] : 0.f;
         am = fmaxf(am, fabsf(gv[i]));
+      }
+      if (c0 + CB < a.C) {
+#pragma unroll
+        for (int i = 0; i < CB; ++i) gn[i] = __ldg(gop + (long long)min(c0 + CB + i, a.C - 1) * plane);
       }
       const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(am));   // non-negative floats order like integers
       if (lane == 0) amax_red[ps & 1][warp] = wm;
       // tap values of this pass's channels
+#ifndef CERB_SPLAT_X_NOX2
       mbar_wait(&xb_full, (uint32_t)(ps & 1));
+#endif
       float tv[CB][4];
 #pragma unroll
       for (int i = 0; i < CB; ++i) {
@@ -147,10 +158,12 @@ flow_warp_bwd_box_kernel(const Args a, const __grid_constant__ CUtensorMap tm_im
         tv[i][2] = lds_f32(pl + BOX_W * 4); tv[i][3] = lds_f32(pl + BOX_W * 4 + 4);
       }
       __syncthreads();   // everyone is done with the x2 window; the pass's maxima are visible; the gradient window is zero
+#ifndef CERB_SPLAT_X_NOX2
       if (tid == 0 && c0 + CB < a.C) {
         mbar_arrive_expect_tx(&xb_full, BOX_BYTES);
         tma_load_4d(smem, &tm_img, &xb_full, box_ox, box_oy, c0 + CB, n2);
       }
+#endif
       const uint32_t cm = max(max(amax_red[ps & 1][0], amax_red[ps & 1][1]), max(amax_red[ps & 1][2], amax_red[ps & 1][3]));
       // cm < 2^(e+1) with e its exponent: scale 2^(22-e) keeps every term below 2^23 and a sum of 128 below 2^30
       const int e = min(max((int)(cm >> 23) - 127, -100), 100);
@@ -193,8 +206,10 @@ flow_warp_bwd_box_kernel(const Args a, const __grid_constant__ CUtensorMap tm_im
       }
 #endif
       __syncthreads();
+#ifndef CERB_SPLAT_X_NOZERO
       if (c0 + CB < a.C)
         for (uint32_t o = (uint32_t)tid * 16u; o < BOX_BYTES; o += NT * 16u) sts128(gbox + o, make_float4(0.f, 0.f, 0.f, 0.f));
+#endif
     }
     if (tid == 0) tma_store_wait_all0();
   } else if (pix_ok) {
