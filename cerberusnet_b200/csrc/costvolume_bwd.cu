@@ -24,8 +24,8 @@ long long* get_trace_buffer();
 // tensor-core backward (costvolume_bwd_tc.cu)
 bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long long s0s[3], const void* x1);
 cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long long s0s[3], int s0_roll, const void* x1,
-                                    const void* x2, const float* flow, const void* out, const void* gout, void* gx1,
-                                    void* gsecond, int gsecond_roll, void* gx2_splat, float* gflow, cudaStream_t stream);
+                                    const void* out, const void* gout, void* gx1, void* gsecond, int gsecond_roll,
+                                    cudaStream_t stream);
 // which backward kernel the fast path takes: -1 automatic, 0 CUDA cores only, 1 tensor cores wherever supported
 // (initialised from CERB_DEBUG_BWD_TC; cerb_debug_set_backward_kernel for tests and the bench)
 static int g_bwd_tc_mode = -2;
@@ -781,23 +781,22 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
           e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
           if (e != cudaSuccess) return e;
         }
-        static const bool fused_splat = getenv("CERB_DEBUG_BWD_TC_BOX") != nullptr;
-        if (flow != nullptr && !fused_splat) {
+        if (flow != nullptr) {
           // gradient wrt the warped map into the workspace (coalesced stores), then the splat as its own kernel
-          e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, x2, nullptr, out, gout, gx1, gwarped, 0, nullptr, nullptr, stream);
+          e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, out, gout, gx1, gwarped, 0, stream);
           if (e == cudaSuccess) {
-            e = splat_backward<T, T>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2, gflow, g.B,
-                g.C, g.H, g.W, g.warp_mode, g.x2roll, stream);
-        if (e != cudaSuccess) return e;
+            e = splat_backward<T, T>((const T*)x2, g.x2s[0], g.x2s[1], g.x2s[2], flow, g.fls[0], g.fls[1], g.fls[2], gwarped, (T*)gx2,
+                                     gflow, g.B, g.C, g.H, g.W, g.warp_mode, g.x2roll, stream);
+            if (e != cudaSuccess) return e;
             count_launches(4);
             return cudaGetLastError();
           }
-        } else
-        e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, x2, flow, out, gout, gx1, flow ? nullptr : gx2,
-                                    g.x2roll, flow ? gx2 : nullptr, gflow, stream);
-        if (e == cudaSuccess) {
-          count_launches(flow != nullptr ? 3 : 1);
-          return cudaGetLastError();
+        } else {
+          e = launch_corr_backward_tc(g, a.s[0], s0s, a.s_roll[0], x1, out, gout, gx1, gx2, g.x2roll, stream);
+          if (e == cudaSuccess) {
+            count_launches(1);
+            return cudaGetLastError();
+          }
         }
         if (e != cudaErrorNotSupported) return e;
       }

@@ -1,5 +1,5 @@
 // costvolume_bwd_tc.cu -- tensor-core (tcgen05 / TMEM) backward of the fused level op for sm_100a: both correlation
-// gradients of a tile as banded GEMMs, the gradient with respect to the warped map splatted in the drain.
+// gradients of a tile as banded GEMMs (the splat of the gradient with respect to the warped map: costvolume_splat.cu).
 //
 // Replaces the same reference sites as costvolume_bwd.cu (correlation_backward_input1/2 correlation_cuda_kernel.cu:97-242,
 // launch loop :326-429; LeakyReluBackward of pwcnet_sfd.py:182; GridSampler2DBackward of UnFlowLoss.py:83-94) for fp32,
@@ -20,9 +20,10 @@
 //     S by four "split" warps (hi = tf32(v) in place, lo = v - hi next to it); three products hi*hi + lo*hi + hi*lo.
 //   * Two 4-warp groups work side by side, one per gradient, each with its own accumulator, band ring and operand stages:
 //     stage Gx of its tile (coalesced loads, LeakyReLU mask applied on the way, private shared-memory columns) -> build 16
-//     band chunks -> stage the next tile's Gx -> drain the accumulator (tcgen05.ld): grad_x1 is stored, the gradient with
-//     respect to the second input is either stored (no flow) or pushed through the four bilinear taps of its position into
-//     grad_x2 (red.global.add) with the flow gradient accumulated over the channels.
+//     band chunks -> stage the next tile's Gx -> drain the accumulators (tcgen05.ld) and store.  With a flow the second
+//     gradient is the one with respect to the warped map: the launcher has it written to the workspace and runs the
+//     shared-memory-window splat (costvolume_splat.cu) afterwards.  (A splat fused into the drain was built and measured --
+//     its three windows left room for only two operand stages -- and removed.)
 // Roles (16 warps): 0-3 gradient wrt x1, 4-7 gradient wrt the second input; per gradient one operand-split warp (8-9), one
 // TMA-issue lane (10-11) and two MMA-issue lanes (12-15).  The two gradients' pipelines are independent of each other and
 // run half a tile period apart.  One CTA per SM, persistent over tiles.
@@ -39,7 +40,6 @@ namespace cerb {
 bool make_tmap_nchw(CUtensorMap* tm, CUtensorMapDataType dt, int esize, const void* base, int W, int H, int C, int B,
                     const long long strides[3], int bx, int by, int bc, bool swizzle128);
 int num_sms_current();
-unsigned long long* get_path_counters();
 long long* get_trace_buffer();
 
 namespace btc {
@@ -58,37 +58,21 @@ constexpr int GPLANES = D2 + 2 * PADPL;
 constexpr uint32_t GS_BYTES = GPLANES * M * 4;  // 44544
 constexpr int MAXSTG = 6, MAXSLOT = 4;
 constexpr int SLOT_COLS = 2 * KU;               // band slot in TMEM: 24 hi + 24 lo columns
-constexpr int NBARS = 2 * (3 * MAXSTG + 2 * MAXSLOT + 2) + 2;   // + the splat's x2-box barrier, + the groups' phase offset
-// splat through shared memory: the taps of a tile's 128 positions land in a BOX_H x BOX_W window of grad_x2 when the flow
-// varies by at most +-SPLAT_MARGIN px inside the tile; CB channels per pass: x2 window in by TMA (tap values for the flow
-// gradient), gradient window accumulated with shared-memory reductions and added to grad_x2 by one TMA reduce
-// (tools/microbench/atomics.cu: scattered red.global 246 G/s = 205 us for this level, coalesced reductions 4 TB/s)
-constexpr int SPLAT_MARGIN = 6, CB = 8;
-constexpr int BOX_H = TY + 2 * SPLAT_MARGIN + 2;                       // 22
-constexpr int BOX_W = (TX + 2 * SPLAT_MARGIN + 2 + 3 + 3) / 4 * 4;     // 36: origin aligned down to 4 elements
-constexpr uint32_t BOX_BYTES = CB * BOX_H * BOX_W * 4;                 // 25344
-static_assert(BOX_BYTES % 128 == 0, "TMA shared-memory alignment");
-
+constexpr int NBARS = 2 * (3 * MAXSTG + 2 * MAXSLOT + 2) + 1;   // + the groups' phase offset
 struct Args {
   Geom g;
   const float* gout;
   const float* out;       // saved activated output (sign only), may be null
   float* gx1;             // contiguous NCHW
-  float* gsecond;         // no flow: gradient wrt x2 (contiguous NCHW, item order of x2)
-  const float* x2;        // with a flow: un-warped second map (tap values for the flow gradient)
-  const float* flow;
-  float* gx2;             // with a flow: splat target (zeroed by the launcher)
-  float* gflow;
+  float* gsecond;         // gradient wrt the second correlation input (contiguous NCHW): grad_x2 itself, or the workspace
   int tiles_x, tiles_y, total_tiles;
   int npad, nstg, nslot;  // N of the MMA, operand stages per gradient, band slots per gradient
   int nacc;               // partial accumulators per gradient (1..3)
   int no_cat;             // debugging: three separate MMAs per K step even with three accumulators
-  int g2_roll;            // no flow: batch roll applied when writing gsecond (x2_batch_roll when it is grad_x2 itself)
+  int g2_roll;            // batch roll applied when writing gsecond (x2_batch_roll when it is grad_x2 itself)
   int s0_roll;            // batch roll applied to the TMA item coordinate of the first gradient's S (x2 itself when no flow)
   int use_pf;             // tensor maps tm_go / tm_o valid: the next tile's grad_out / out planes are prefetched into L2
-  int use_box;            // splat through shared-memory windows (tensor maps tm_x2 / tm_gx2 valid, 3 boxes in shared memory)
   long long* dbg;         // optional per-CTA clock64() trace (cerb_debug_set_trace_buffer; -DCERB_BTC_TRACE), 192 slots per CTA
-  unsigned long long* path_ctr;   // [1] tiles splatted through the box, [2] tiles on the direct path (cerb_debug_set_path_counters)
 };
 
 #ifdef CERB_BTC_TRACE
@@ -142,21 +126,8 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {   //
   lo = v - hi;
 }
 __device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t parity) { mbar_wait_hint(bar, parity, 20000); }
-__device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-// shared-memory fp32 atomics are compare-and-swap loops (SASS ATOMS.CAST.SPIN: measured 18 K cycles per pass of 4096 here);
-// 32-bit integer ones are native (ATOMS.ADD): the gradient window is accumulated in fixed point -- scale = a power of two
-// chosen from the tile's largest contribution so that 128 of them cannot overflow, i.e. 2^-23 of that contribution per
-// term, far inside the fp32 parity bar -- and converted in place before the TMA reduce.  Integer sums are associative:
-// the window is bit-reproducible whatever the order of the reductions.
-__device__ __forceinline__ void red_shared_s32(uint32_t addr, int v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {   // tile -> L2
   asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-               : "memory");
-}
-// TMA: 4-D tiled reduction shared -> global, element-wise add (SASS: UTMAREDG); out-of-range elements are clipped
-__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
-               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 
@@ -168,7 +139,6 @@ __device__ __forceinline__ int plane_idx(int t) { return (t & ~31) | ((t + 8 * (
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, const __grid_constant__ CUtensorMap tm_s1,
-                   const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_gx2,
                    const __grid_constant__ CUtensorMap tm_go, const __grid_constant__ CUtensorMap tm_o) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -177,8 +147,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
   const int npad = a.npad, nstg = a.nstg, nslot = a.nslot, nacc = a.nacc;
   const uint32_t STG = (uint32_t)npad * 128u;                       // one operand tile (hi or lo) of a chunk
   const uint32_t OFF_GS = 2u * (uint32_t)nstg * 2u * STG;           // Gx buffers of the two groups
-  const uint32_t OFF_BOX = OFF_GS + 2u * GS_BYTES;                  // x2 window, two gradient windows (use_box)
-  const uint32_t OFF_BAR = OFF_BOX + (a.use_box ? 3u * BOX_BYTES : 0u);
+  const uint32_t OFF_BAR = OFF_GS + 2u * GS_BYTES;
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
   // per gradient X: raw_full[MAXSTG] s_full[MAXSTG] s_empty[MAXSTG] band_full[MAXSLOT] band_empty[MAXSLOT] d_full d_empty
   auto BAR = [&](int X, int which, int i) -> uint64_t* {
@@ -187,11 +156,8 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
     return bars + base + (which < 5 ? off + i : 3 * MAXSTG + 2 * MAXSLOT + (which - 5));
   };
   enum { RAW_FULL = 0, S_FULL = 1, S_EMPTY = 2, BAND_FULL = 3, BAND_EMPTY = 4, D_FULL = 5, D_EMPTY = 6 };
-  uint64_t* xb_full = bars + NBARS - 1;
-  uint64_t* offset_bar = bars + NBARS - 2;
+  uint64_t* offset_bar = bars + NBARS - 1;
   uint32_t* tmem_slot = (uint32_t*)(smem + OFF_BAR + NBARS * 8);
-  int* bbox_red = (int*)(smem + OFF_BAR + NBARS * 8 + 24);   // [4 warps][xmin, xmax, ymin, ymax]
-  uint32_t* amax_red = (uint32_t*)(smem + OFF_BAR + NBARS * 8 + 24 + 64);   // [4 warps] largest |gradient| of the tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
@@ -208,15 +174,8 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
       mbar_init(BAR(X, D_FULL, 0), min(nacc, 2));
       mbar_init(BAR(X, D_EMPTY, 0), GROUP_WARPS);
     }
-    mbar_init(xb_full, 1);
     mbar_init(offset_bar, GROUP_WARPS);
     fence_barrier_init();
-    if (a.use_box) {
-      tma_prefetch_desc(&tm_x2);
-      tma_prefetch_desc(&tm_gx2);
-    }
-    tma_prefetch_desc(&tm_s0);
-    tma_prefetch_desc(&tm_s1);
   }
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
@@ -319,7 +278,6 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
 
     int cnt = 0;   // band chunks built so far (all tiles)
     int ti = 0;
-    int xcnt = 0, gcnt = 0;   // x2 windows loaded / gradient windows reduced so far (splat)
     if ((int)blockIdx.x < a.total_tiles) stage_g(blockIdx.x);
     named_bar_sync(bar_id, 128);
 #ifndef CERB_BTC_NO_OFFSET
@@ -387,45 +345,6 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
           for (int i = 0; i < 8; ++i) v[i] += w[i];
         }
       };
-      const bool splat = X == 1 && a.flow != nullptr;
-      // ---- splat: sampling data of this position; do the tile's taps fit one shared-memory window?
-      float sx = 0.f, sy = 0.f, wx1 = 0.f, wx0 = 0.f, wy1 = 0.f, wy0 = 0.f;
-      bool inx = false, iny = false, bx1 = false, by1 = false, fits = false;
-      int ix0 = 0, iy0 = 0, box_ox = 0, box_oy = 0;
-      const int n_x2 = x2_item(g, n);
-      if (splat) {
-        const int yc = min(y, g.H - 1), xc = min(x, g.W - 1);
-        const float* fp = a.flow + (long long)n * g.fls[0] + (long long)yc * g.fls[2] + xc;
-        sx = sample_pos(xc, __ldg(fp), g.W, g.warp_mode, inx);
-        sy = sample_pos(yc, __ldg(fp + g.fls[1]), g.H, g.warp_mode, iny);
-        const float fx = floorf(sx), fy = floorf(sy);
-        ix0 = (int)fx; iy0 = (int)fy;
-        wx1 = fx + 1.f - sx; wx0 = sx - fx; wy1 = fy + 1.f - sy; wy0 = sy - fy;
-        bx1 = ix0 + 1 < g.W; by1 = iy0 + 1 < g.H;
-        if (a.use_box) {
-          int xmin = pix_ok ? ix0 : 0x7fffffff, xmax = pix_ok ? ix0 + 1 : -0x7fffffff;
-          int ymin = pix_ok ? iy0 : 0x7fffffff, ymax = pix_ok ? iy0 + 1 : -0x7fffffff;
-          xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-          ymin = __reduce_min_sync(0xffffffffu, ymin); ymax = __reduce_max_sync(0xffffffffu, ymax);
-          if (lane == 0) *reinterpret_cast<int4*>(bbox_red + 4 * wq) = make_int4(xmin, xmax, ymin, ymax);
-          named_bar_sync(bar_id, 128);
-          xmin = 0x7fffffff; xmax = -0x7fffffff; ymin = 0x7fffffff; ymax = -0x7fffffff;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int4 b = *reinterpret_cast<const int4*>(bbox_red + 4 * w);
-            xmin = min(xmin, b.x); xmax = max(xmax, b.y);
-            ymin = min(ymin, b.z); ymax = max(ymax, b.w);
-          }
-          box_ox = xmin & ~3;   // TMA box starts are 16-byte aligned
-          box_oy = ymin;
-          fits = xmin <= xmax && xmax - box_ox < BOX_W && ymax - box_oy < BOX_H;
-          if (fits && gt == 0) {   // x2 window of the first channel pass
-            mbar_arrive_expect_tx(xb_full, BOX_BYTES);
-            tma_load_4d(smem + OFF_BOX, &tm_x2, xb_full, box_ox, box_oy, 0, n_x2);
-          }
-          if (gt == 0 && a.path_ctr != nullptr) atomicAdd(&a.path_ctr[fits ? 1 : 2], 1ull);
-        }
-      }
       if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 3);
       // ---- the next tile's Gx while this tile's last MMAs run
       if (tile + (int)gridDim.x < a.total_tiles) stage_g(tile + gridDim.x);
@@ -440,7 +359,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(X, D_EMPTY, 0));
       };
-      if (!splat) {
+      {
         int n_dst = X == 0 ? n : n + a.g2_roll;
         if (n_dst >= g.B) n_dst -= g.B;
         float* dst = (X == 0 ? a.gx1 : a.gsecond) + (long long)n_dst * g.C * plane + (long long)min(y, g.H - 1) * g.W + min(x, g.W - 1);
@@ -453,130 +372,6 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
             for (int i = 0; i < 8; ++i)
               if (c0 + i < g.C) dst[(long long)(c0 + i) * plane] = v[i] * inv_c;
           }
-        }
-      } else {
-        // gradient wrt the warped map -> through the bilinear taps of this position into grad_x2; flow gradient over channels
-        const float w_nw = wx1 * wy1, w_ne = bx1 ? wx0 * wy1 : 0.f, w_sw = by1 ? wx1 * wy0 : 0.f, w_se = (bx1 && by1) ? wx0 * wy0 : 0.f;
-        float gix = 0.f, giy = 0.f;
-        if (fits) {
-          // taps inside the window (byte offset within one channel plane of the box)
-          const uint32_t t_nw = (uint32_t)(((iy0 - box_oy) * BOX_W + (ix0 - box_ox)) * 4);
-          const uint32_t xbox = sbase + OFF_BOX;
-          // fixed-point scale of the tile: largest |gradient| over positions and channels (a first sweep over the accumulator)
-          float fs, ifs;
-          {
-            float am = 0.f;
-            for (int c0 = 0; c0 < npad; c0 += 8) {
-              float v[8];
-              ld_acc8(c0, v);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) am = fmaxf(am, fabsf(v[i]));
-            }
-            const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(am * inv_c));   // non-negative floats order like integers
-            if (lane == 0) amax_red[wq] = wm;
-            named_bar_sync(bar_id, 128);
-            const uint32_t cm = max(max(amax_red[0], amax_red[1]), max(amax_red[2], amax_red[3]));
-            // cm < 2^(e+1) with e its exponent: scale 2^(22-e) keeps every term below 2^23 and a sum of 128 below 2^30
-            const int e = min(max((int)(cm >> 23) - 127, -100), 100);
-            fs = __uint_as_float((uint32_t)(127 + 22 - e) << 23);
-            ifs = __uint_as_float((uint32_t)(127 - 22 + e) << 23);
-          }
-          for (int c0 = 0; c0 < npad; c0 += CB) {
-            float v[8];
-            ld_acc8(c0, v);
-            if (c0 + CB >= npad) release_d();
-            // tap values of this pass's channels
-            wait_bar(xb_full, (uint32_t)(xcnt & 1));
-            ++xcnt;
-            float tv[CB][4];
-#pragma unroll
-            for (int i = 0; i < CB; ++i) {
-              const uint32_t pl = xbox + (uint32_t)(i * BOX_H * BOX_W * 4) + (pix_ok ? t_nw : 0u);
-              tv[i][0] = lds_f32(pl); tv[i][1] = lds_f32(pl + 4);
-              tv[i][2] = lds_f32(pl + BOX_W * 4); tv[i][3] = lds_f32(pl + BOX_W * 4 + 4);
-            }
-            // the gradient window of two passes ago has been read by its reduce; everyone is done with the x2 window
-            if (gt == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            named_bar_sync(bar_id, 128);
-            const uint32_t gbox = sbase + OFF_BOX + (uint32_t)(1 + (gcnt & 1)) * BOX_BYTES;
-            for (uint32_t o = (uint32_t)gt * 16u; o < BOX_BYTES; o += 128u * 16u) sts128(gbox + o, make_float4(0.f, 0.f, 0.f, 0.f));
-            if (gt == 0 && c0 + CB < npad) {
-              mbar_arrive_expect_tx(xb_full, BOX_BYTES);
-              tma_load_4d(smem + OFF_BOX, &tm_x2, xb_full, box_ox, box_oy, c0 + CB, n_x2);
-            }
-            named_bar_sync(bar_id, 128);
-            if (pix_ok) {
-#pragma unroll
-              for (int i = 0; i < CB; ++i) {
-                const float gv = (c0 + i < g.C) ? v[i] * inv_c : 0.f;
-                const float gs = gv * fs;
-                const uint32_t pl = gbox + (uint32_t)(i * BOX_H * BOX_W * 4) + t_nw;
-                red_shared_s32(pl, __float2int_rn(gs * w_nw));
-                red_shared_s32(pl + 4, __float2int_rn(gs * w_ne));
-                red_shared_s32(pl + BOX_W * 4, __float2int_rn(gs * w_sw));
-                red_shared_s32(pl + BOX_W * 4 + 4, __float2int_rn(gs * w_se));
-                const float v_nw = tv[i][0], v_ne = bx1 ? tv[i][1] : 0.f, v_sw = by1 ? tv[i][2] : 0.f;
-                const float v_se = (bx1 && by1) ? tv[i][3] : 0.f;
-                gix += gv * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
-                giy += gv * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
-              }
-            }
-            named_bar_sync(bar_id, 128);
-            // fixed point -> fp32 in place
-            for (uint32_t o = (uint32_t)gt * 16u; o < BOX_BYTES; o += 128u * 16u) {
-              const float4 q = lds128(gbox + o);
-              sts128(gbox + o, make_float4((float)__float_as_int(q.x) * ifs, (float)__float_as_int(q.y) * ifs,
-                                           (float)__float_as_int(q.z) * ifs, (float)__float_as_int(q.w) * ifs));
-            }
-            fence_proxy_async_smem();   // generic-proxy writes -> visible to the TMA's reads
-            named_bar_sync(bar_id, 128);
-            if (gt == 0) {
-              tma_reduce_add_4d(&tm_gx2, gbox, box_ox, box_oy, c0, n_x2);
-              tma_store_commit();
-            }
-            ++gcnt;
-          }
-        } else {
-          const Taps tp_in = make_taps(sx, sy, g.H, g.W, g.x2s[2]);
-          const Taps tp_out = make_taps(sx, sy, g.H, g.W, g.W);
-          const float* x2n = a.x2 + (long long)n_x2 * g.x2s[0];
-          float* gx2n = a.gx2 + (long long)n_x2 * g.C * plane;
-          for (int c0 = 0; c0 < npad; c0 += 8) {
-            float v[8];
-            ld_acc8(c0, v);
-            if (c0 + 8 >= npad) release_d();
-            if (pix_ok) {
-              float tv[8][4];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float* pch = x2n + (long long)min(c0 + i, g.C - 1) * g.x2s[1];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) tv[i][q] = __ldg(pch + tp_in.off[q]);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (c0 + i < g.C) {
-                  const float gv = v[i] * inv_c;
-                  float* gp = gx2n + (long long)(c0 + i) * plane;
-                  if (tp_out.w[0] != 0.f) red_add(gp + tp_out.off[0], gv * tp_out.w[0]);
-                  if (tp_out.w[1] != 0.f) red_add(gp + tp_out.off[1], gv * tp_out.w[1]);
-                  if (tp_out.w[2] != 0.f) red_add(gp + tp_out.off[2], gv * tp_out.w[2]);
-                  if (tp_out.w[3] != 0.f) red_add(gp + tp_out.off[3], gv * tp_out.w[3]);
-                  const float v_nw = tv[i][0];
-                  const float v_ne = bx1 ? tv[i][1] : 0.f;
-                  const float v_sw = by1 ? tv[i][2] : 0.f;
-                  const float v_se = (bx1 && by1) ? tv[i][3] : 0.f;
-                  gix += gv * ((v_ne - v_nw) * wy1 + (v_se - v_sw) * wy0);
-                  giy += gv * ((v_sw - v_nw) * wx1 + (v_se - v_ne) * wx0);
-                }
-              }
-            }
-          }
-        }
-        if (pix_ok) {
-          float* gf = a.gflow + (long long)n * 2 * plane + (long long)y * g.W + x;
-          gf[0] = inx ? gix * pos_scale(g.W, g.warp_mode) : 0.f;
-          gf[plane] = iny ? giy * pos_scale(g.H, g.warp_mode) : 0.f;
         }
       }
       if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 6);
@@ -768,14 +563,15 @@ bool tc_backward_supported(const Geom& g, int dtype, const void* s0, const long 
   return true;
 }
 
+// gsecond: contiguous NCHW destination of the gradient with respect to the second correlation input -- grad_x2 itself
+// (gsecond_roll = x2_batch_roll) or, with a flow, the workspace the splat kernel reads (roll 0)
 cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long long s0s[3], int s0_roll, const void* x1,
-                                    const void* x2, const float* flow, const void* out, const void* gout, void* gx1,
-                                    void* gsecond, int gsecond_roll, void* gx2_splat, float* gflow, cudaStream_t stream) {
+                                    const void* out, const void* gout, void* gx1, void* gsecond, int gsecond_roll,
+                                    cudaStream_t stream) {
   btc::Args a;
   a.g = g;
   a.gout = (const float*)gout; a.out = (const float*)out;
   a.gx1 = (float*)gx1; a.gsecond = (float*)gsecond;
-  a.x2 = (const float*)x2; a.flow = flow; a.gx2 = (float*)gx2_splat; a.gflow = gflow;
   a.tiles_x = (g.W + btc::TX - 1) / btc::TX;
   a.tiles_y = (g.H + btc::TY - 1) / btc::TY;
   a.total_tiles = g.B * a.tiles_x * a.tiles_y;
@@ -792,32 +588,16 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
   if (a.nslot > btc::MAXSLOT) a.nslot = btc::MAXSLOT;
   static const bool no_cat = getenv("CERB_DEBUG_BWD_TC_NOCAT") != nullptr;
   a.no_cat = no_cat ? 1 : 0;
-  a.path_ctr = get_path_counters();
   a.dbg = get_trace_buffer();
-  CUtensorMap tm0, tm1, tmx, tmg;
+  CUtensorMap tm0, tm1;
   memset(&tm0, 0, sizeof(tm0));
   memset(&tm1, 0, sizeof(tm1));
-  memset(&tmx, 0, sizeof(tmx));
-  memset(&tmg, 0, sizeof(tmg));
   if (!make_tmap_nchw(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, s0, g.W, g.H, g.C, g.B, s0s, btc::KBOX, 1, a.npad, true) ||
       !make_tmap_nchw(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x1, g.W, g.H, g.C, g.B, g.x1s, btc::KBOX, 1, a.npad, true))
     return cudaErrorNotSupported;
-  // splat through shared-memory windows: x2 (tap values) and grad_x2 (contiguous) as TMA tensors, three windows of shared memory
-  a.use_box = 0;
-  // (off by default: the three windows leave room for only two operand stages per gradient, and the operand pipeline --
-  // commit -> TMA -> split -> MMA, ~4 K cycles per round trip in the clock64 trace -- then bounds the tile; the launcher
-  // runs the splat as its own kernel instead.  CERB_DEBUG_BWD_TC_BOX=1 turns the fused form on.)
-  static const bool no_box = getenv("CERB_DEBUG_BWD_TC_BOX") == nullptr;
-  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::NBARS * 8 + 24 + 64 + 16 + 1024;
+  // shared memory: the two Gx buffers, barriers, and as many operand stages (hi + lo tile) per gradient as fit
+  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::NBARS * 8 + 16 + 1024;
   const size_t stage = 2 * (size_t)a.npad * 128;
-  if (flow != nullptr && !no_box) {
-    const long long gs[3] = {(long long)g.C * g.H * g.W, (long long)g.H * g.W, (long long)g.W};
-    const size_t need = fixed + 3 * (size_t)btc::BOX_BYTES + 2 * 2 * stage;   // at least two operand stages per gradient
-    if (need <= 227 * 1024 &&
-        make_tmap_nchw(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x2, g.W, g.H, g.C, g.B, g.x2s, btc::BOX_W, btc::BOX_H, btc::CB, false) &&
-        make_tmap_nchw(&tmg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gx2_splat, g.W, g.H, g.C, g.B, gs, btc::BOX_W, btc::BOX_H, btc::CB, false))
-      a.use_box = 1;
-  }
   CUtensorMap tmgo, tmo;
   memset(&tmgo, 0, sizeof(tmgo));
   memset(&tmo, 0, sizeof(tmo));
@@ -826,11 +606,10 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
              make_tmap_nchw(&tmgo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, gout, g.outW, g.outH, g.D2, g.B, g.os, btc::KU, btc::HY, g.D2, false) &&
              (out == nullptr ||
               make_tmap_nchw(&tmo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, out, g.outW, g.outH, g.D2, g.B, g.os, btc::KU, btc::HY, g.D2, false));
-  const size_t boxes = a.use_box ? 3 * (size_t)btc::BOX_BYTES : 0;
-  a.nstg = (int)((227 * 1024 - fixed - boxes) / (2 * stage));
+  a.nstg = (int)((227 * 1024 - fixed) / (2 * stage));
   if (a.nstg > btc::MAXSTG) a.nstg = btc::MAXSTG;
   if (a.nslot < 2 || a.nstg < 2) return cudaErrorNotSupported;
-  const size_t smem = 2 * (size_t)a.nstg * stage + boxes + fixed;
+  const size_t smem = 2 * (size_t)a.nstg * stage + fixed;
   auto kern = btc::corr_bwd_tc_kernel;
   static unsigned long long attr_devs = 0ull;   // function attributes are per device
   {
@@ -845,7 +624,7 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
   }
   int grid = num_sms_current();
   if (grid > a.total_tiles) grid = a.total_tiles;
-  kern<<<grid, btc::NTHREADS, smem, stream>>>(a, tm0, tm1, tmx, tmg, tmgo, tmo);
+  kern<<<grid, btc::NTHREADS, smem, stream>>>(a, tm0, tm1, tmgo, tmo);
   return cudaGetLastError();
 }
 
