@@ -769,14 +769,14 @@ static cudaError_t launch_bwd_t(const Geom& g, const void* x1, const void* x2, c
     static const bool unfused = getenv("CERB_DEBUG_BWD_UNFUSED") != nullptr;
     const bool ty4 = force_ty ? force_ty == 4 : true;
     // Tensor-core kernel (costvolume_bwd_tc.cu): fp32, md = pad = 4, C <= 128, 16-byte aligned rows.  Taken automatically from
-    // 1024 tiles of 8 x 16 and 48 channels up, where it measured faster than the fused CUDA-core kernel (HRNet level 3, batch 8:
-    // 476 vs 508 us; with 32 channels or at 512 tiles the two are within a few per cent of each other either way);
-    // cerb_debug_set_backward_kernel / CERB_DEBUG_BWD_TC: 1 forces it wherever it is supported, 0 turns it off
+    // 512 tiles of 8 x 16 and 48 channels up, where it measured faster than the fused CUDA-core kernel (batch 8: HRNet level 3
+    // 459 vs 508 us, HRNet level 2 250 vs 272, PWC level 3 191 vs 195; with 32 channels the two are within a few per cent of
+    // each other either way); cerb_debug_set_backward_kernel / CERB_DEBUG_BWD_TC: 1 forces it wherever supported, 0 turns it off
     if (std::is_same<T, float>::value && !unfused && !force_ty) {
       const int tc_mode = get_backward_kernel_mode();
       const long long s0s[3] = {a.s_ns[0], a.s_cs[0], a.s_hs[0]};
       const long long tiles = (long long)g.B * ((g.H + 7) / 8) * ((g.W + 15) / 16);
-      if (tc_mode != 0 && (tc_mode == 1 || (tiles >= 1024 && g.C >= 48)) && tc_backward_supported(g, CERB_F32, a.s[0], s0s, x1)) {
+      if (tc_mode != 0 && (tc_mode == 1 || (tiles >= 512 && g.C >= 48)) && tc_backward_supported(g, CERB_F32, a.s[0], s0s, x1)) {
         if (flow != nullptr) {
           e = cudaMemsetAsync(gx2, 0, (size_t)in_elems * sizeof(T), stream);
           if (e != cudaSuccess) return e;
