@@ -56,6 +56,7 @@ constexpr int NTHREADS = (MMA_WARP + MMA_WARPS) * 32;   // 512: 16 warps (regist
 constexpr int PADPL = 3;                        // zero planes before / after the 81 of a Gx buffer (shifted reads)
 constexpr int GPLANES = D2 + 2 * PADPL;
 constexpr uint32_t GS_BYTES = GPLANES * M * 4;  // 44544
+constexpr uint32_t ZERO_BYTES = 12 * M * 4;     // twelve zero planes: what a lane reads for a halo row outside its 9 displacement rows
 constexpr int MAXSTG = 6, MAXSLOT = 4;
 constexpr int SLOT_COLS = 2 * KU;               // band slot in TMEM: 24 hi + 24 lo columns
 constexpr int NBARS = 2 * (3 * MAXSTG + 2 * MAXSLOT + 2) + 1;   // + the groups' phase offset
@@ -147,7 +148,8 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
   const int npad = a.npad, nstg = a.nstg, nslot = a.nslot, nacc = a.nacc;
   const uint32_t STG = (uint32_t)npad * 128u;                       // one operand tile (hi or lo) of a chunk
   const uint32_t OFF_GS = 2u * (uint32_t)nstg * 2u * STG;           // Gx buffers of the two groups
-  const uint32_t OFF_BAR = OFF_GS + 2u * GS_BYTES;
+  const uint32_t OFF_ZERO = OFF_GS + 2u * GS_BYTES;
+  const uint32_t OFF_BAR = OFF_ZERO + ZERO_BYTES;
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
   // per gradient X: raw_full[MAXSTG] s_full[MAXSTG] s_empty[MAXSTG] band_full[MAXSLOT] band_empty[MAXSLOT] d_full d_empty
   auto BAR = [&](int X, int which, int i) -> uint64_t* {
@@ -182,7 +184,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // the pad planes of the Gx buffers are read (and discarded) by the shifted band loads: keep them finite
-  for (int i = tid; i < 2 * (int)(GS_BYTES / 4); i += NTHREADS) reinterpret_cast<float*>(smem + OFF_GS)[i] = 0.f;
+  for (int i = tid; i < (int)((2 * GS_BYTES + ZERO_BYTES) / 4); i += NTHREADS) reinterpret_cast<float*>(smem + OFF_GS)[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -286,30 +288,37 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
     // both then wait on memory at the same time.  The second group starts building when the first has built its first tile.
     if (X == 1) wait_bar(offset_bar, 0u);
 #endif
+    // band ring: slot index and phase parity kept incrementally, barrier / column bases hoisted (the chunk loop is bound by
+    // instruction issue: ~230 instructions per chunk and thread)
+    uint64_t* const band_full0 = BAR(X, BAND_FULL, 0);
+    uint64_t* const band_empty0 = BAR(X, BAND_EMPTY, 0);
+    const uint32_t col0 = tlane + RING0 + (uint32_t)(X * nslot * SLOT_COLS + 4 * wq);
+    const uint32_t zero_u32 = sbase + OFF_ZERO + 4u * (uint32_t)bidx;
+    int slot = 0;
+    uint32_t bphase = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
       if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 0);
       // ---- 16 band chunks: chunk r = halo row r; this lane's entries are Gx[(r - bpy, k - res)] at columns 4 wq + k
 #pragma unroll 1
       for (int r = 0; r < HY; ++r, ++cnt) {
-        const int slot = cnt % nslot, use = cnt / nslot;
         const int ey = r - bpy;
         const bool rowv = ey >= 0 && ey < D;
-        const int eyc = min(max(ey, 0), D - 1);
-        const uint32_t base = gs_u32 + 4u * (uint32_t)((PADPL + eyc * D - res) * M + bidx);
+        // a halo row outside this lane's 9 displacement rows reads the zero planes instead (one select on the address)
+        const uint32_t base = rowv ? gs_u32 + 4u * (uint32_t)((PADPL + ey * D - res) * M + bidx) : zero_u32;
         float v[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) v[k] = lds_f32(base + (uint32_t)k * (M * 4));
 #pragma unroll
         for (int k = 0; k < 12; ++k) {
-          const bool colv = k >= 3 && k <= 8 ? true : (k < 3 ? res <= k : res >= k - 8);   // 0 <= k - res <= 8
-          v[k] = (rowv && colv) ? v[k] : 0.f;
+          if (k < 3) v[k] = res <= k ? v[k] : 0.f;             // 0 <= k - res <= 8: columns 3..8 are always inside
+          if (k > 8) v[k] = res >= k - 8 ? v[k] : 0.f;
         }
         float hi[12], lo[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) split_tf32(v[k], hi[k], lo[k]);
-        wait_bar(BAR(X, BAND_EMPTY, slot), (uint32_t)((use & 1) ^ 1));
+        wait_bar(band_empty0 + slot, bphase ^ 1u);
         tc_fence_after();
-        const uint32_t col = tlane + RING0 + (uint32_t)((X * nslot + slot) * SLOT_COLS + 4 * wq);
+        const uint32_t col = col0 + (uint32_t)(slot * SLOT_COLS);
 #pragma unroll
         for (int k = 0; k < 12; k += 4) {
           tmem_st4(col + (uint32_t)k, hi[k], hi[k + 1], hi[k + 2], hi[k + 3]);
@@ -318,8 +327,9 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(X, BAND_FULL, slot));
+        if (lane == 0) mbar_arrive(band_full0 + slot);
         if ((tid & 127) == 0 && r == 3) BT_TRACE(ti, X * 12 + 1);
+        if (++slot == nslot) { slot = 0; bphase ^= 1u; }
       }
       if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 2);
 #ifndef CERB_BTC_NO_OFFSET
@@ -596,7 +606,7 @@ cudaError_t launch_corr_backward_tc(const Geom& g, const void* s0, const long lo
       !make_tmap_nchw(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x1, g.W, g.H, g.C, g.B, g.x1s, btc::KBOX, 1, a.npad, true))
     return cudaErrorNotSupported;
   // shared memory: the two Gx buffers, barriers, and as many operand stages (hi + lo tile) per gradient as fit
-  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::NBARS * 8 + 16 + 1024;
+  const size_t fixed = 2 * (size_t)btc::GS_BYTES + btc::ZERO_BYTES + btc::NBARS * 8 + 16 + 1024;
   const size_t stage = 2 * (size_t)a.npad * 128;
   CUtensorMap tmgo, tmo;
   memset(&tmgo, 0, sizeof(tmgo));
