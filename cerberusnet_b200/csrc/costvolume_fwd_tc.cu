@@ -62,8 +62,12 @@ constexpr int SLOTS = 4;                              // K steps per 128-byte op
 constexpr int RS_MAX = 3;                             // raw boxes in flight (fp32: 3, 16-bit: 2)
 constexpr int EPI_WARPS = 8, GATHER_WARPS = 12, A_WARPS = 4;   // drain / gather / (of the drain warps) x1 staging
 constexpr int GATHER_THREADS = GATHER_WARPS * 32;
-constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, TMA_WARP = MMA_WARP + 1;
-constexpr int NTHREADS = (TMA_WARP + 1) * 32;         // 704
+constexpr int MMA_WARP = EPI_WARPS + GATHER_WARPS, TMA_WARP = MMA_WARP + 1, MMA_WARP2 = TMA_WARP + 1;
+#ifndef CERB_TC_MMA_WARPS
+#define CERB_TC_MMA_WARPS 2
+#endif
+constexpr int MMA_ISSUERS = CERB_TC_MMA_WARPS;        // 2: one issuing warp per accumulator half (an MMA costs its issuing thread ~140 cycles)
+constexpr int NTHREADS = (TMA_WARP + MMA_ISSUERS) * 32;   // 736
 constexpr uint32_t B_BYTES = N * 128, A_BYTES = M * 128;
 constexpr uint32_t OFF_BHI = 0;
 constexpr uint32_t TMEM_A = N;                        // fp32: x1 operand in TMEM columns 384 + 16 slot (8 hi, 8 lo)
@@ -287,13 +291,13 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
     for (int s = 0; s < SLOTS; ++s) {
       mbar_init(&a_full[s], A_WARPS);
       mbar_init(&b_full[s], GATHER_WARPS);
-      mbar_init(&slot_empty[s], 1);
+      mbar_init(&slot_empty[s], MMA_ISSUERS);
     }
     for (int s = 0; s < RS; ++s) {
       mbar_init(&raw_full[s], 1);
       mbar_init(&raw_empty[s], GATHER_WARPS);
     }
-    mbar_init(d_full, 1);
+    mbar_init(d_full, MMA_ISSUERS);
     mbar_init(d_empty, EPI_WARPS);
     mbar_init(&bbox_full[0], GATHER_WARPS);
     mbar_init(&bbox_full[1], GATHER_WARPS);
@@ -751,53 +755,53 @@ warp_corr_fwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_raw
       }
       cur = nxt;
     }
-  } else if (warp == MMA_WARP) {
-    // =========================== MMA issue: one lane ===========================
+  } else if (warp == MMA_WARP || warp == MMA_WARP2) {
+    // =========================== MMA issue: one lane per accumulator half ===========================
+    // (the two N = 192 halves of the accumulator are independent; issuing a tcgen05.mma costs the thread ~140 cycles --
+    // measured on the backward kernel, costvolume_bwd_tc.cu -- so two issuing warps shorten the MMA -> drain chain)
     if (lane == 0) {
+      const int h0 = MMA_ISSUERS == 2 ? (warp == MMA_WARP ? 0 : 1) : 0, h1 = MMA_ISSUERS == 2 ? h0 + 1 : 2;
       // instruction descriptor: D fp32 (bit 4), A / B format (bits 7-9 / 10-12: tf32 = 2; kind::f16: fp16 = 0, bf16 = 1), both
       // K-major, N = 192, M = 128
       constexpr uint32_t fmt = F32 ? 2u : (std::is_same<T, __half>::value ? 0u : 1u);
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-      const uint64_t d_bh0 = make_desc(sbase + OFF_BHI), d_bh1 = make_desc(sbase + OFF_BHI + NH * 128);
-      const uint64_t d_bl0 = make_desc(sbase + OFF_BLO), d_bl1 = make_desc(sbase + OFF_BLO + NH * 128);
       const uint64_t d_a = make_desc(sbase + OFF_A);                                                     // (16-bit only)
       int kc = 0, ti = 0;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ti) {
         tc_wait(d_empty, (uint32_t)((ti & 1) ^ 1));   // previous tile drained
         tc_fence_after();
-        TC_TRACE(ti, 20);
+        if (warp == MMA_WARP) TC_TRACE(ti, 20);
         for (int ks = 0; ks < nks; ++ks, ++kc) {
           const int slot = kc & (SLOTS - 1), use = kc >> 2;
           tc_wait(&a_full[slot], (uint32_t)(use & 1));
           tc_wait(&b_full[slot], (uint32_t)(use & 1));
           tc_fence_after();
-          if (ks < 4) TC_TRACE(ti, 21 + ks);
+          if (warp == MMA_WARP && ks < 4) TC_TRACE(ti, 21 + ks);
           const uint64_t ko = (uint64_t)(2 * slot);   // 32 bytes per K step inside the 128-byte swizzle atom
           const uint32_t acc = ks > 0 ? 1u : 0u;
 #ifndef CERB_TCX_NOMMA
-          if constexpr (F32) {
-            const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
-            umma_tf32_ta(tmem, a_hi, d_bh0 + ko, idesc, acc);
-            umma_tf32_ta(tmem, a_lo, d_bh0 + ko, idesc, 1u);
-            umma_tf32_ta(tmem, a_hi, d_bl0 + ko, idesc, 1u);
-            umma_tf32_ta(tmem + NH, a_hi, d_bh1 + ko, idesc, acc);
-            umma_tf32_ta(tmem + NH, a_lo, d_bh1 + ko, idesc, 1u);
-            umma_tf32_ta(tmem + NH, a_hi, d_bl1 + ko, idesc, 1u);
-          } else {
-            umma_f16(tmem, d_a + ko, d_bh0 + ko, idesc, acc);
-            umma_f16(tmem, d_a + ko, d_bl0 + ko, idesc, 1u);
-            umma_f16(tmem + NH, d_a + ko, d_bh1 + ko, idesc, acc);
-            umma_f16(tmem + NH, d_a + ko, d_bl1 + ko, idesc, 1u);
+          for (int h = h0; h < h1; ++h) {
+            const uint64_t d_bh = make_desc(sbase + OFF_BHI + (uint32_t)h * NH * 128), d_bl = make_desc(sbase + OFF_BLO + (uint32_t)h * NH * 128);
+            const uint32_t d_t = tmem + (uint32_t)h * NH;
+            if constexpr (F32) {
+              const uint32_t a_hi = tmem + TMEM_A + (uint32_t)slot * 16u, a_lo = a_hi + 8u;
+              umma_tf32_ta(d_t, a_hi, d_bh + ko, idesc, acc);
+              umma_tf32_ta(d_t, a_lo, d_bh + ko, idesc, 1u);
+              umma_tf32_ta(d_t, a_hi, d_bl + ko, idesc, 1u);
+            } else {
+              umma_f16(d_t, d_a + ko, d_bh + ko, idesc, acc);
+              umma_f16(d_t, d_a + ko, d_bl + ko, idesc, 1u);
+            }
           }
 #endif
           umma_commit(&slot_empty[slot]);
         }
         umma_commit(d_full);
-        TC_TRACE(ti, 25);
+        if (warp == MMA_WARP) TC_TRACE(ti, 25);
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == TMA_WARP) {
     // =========================== raw x2 boxes by TMA: one lane ===========================
     if (a.use_raw && lane == 0) {
       int rc = 0, ti = 0;
