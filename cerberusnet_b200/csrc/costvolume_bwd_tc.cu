@@ -278,7 +278,6 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
       }
     };
 
-    int cnt = 0;   // band chunks built so far (all tiles)
     int ti = 0;
     if ((int)blockIdx.x < a.total_tiles) stage_g(blockIdx.x);
     named_bar_sync(bar_id, 128);
@@ -300,7 +299,7 @@ corr_bwd_tc_kernel(const Args a, const __grid_constant__ CUtensorMap tm_s0, cons
       if ((tid & 127) == 0) BT_TRACE(ti, X * 12 + 0);
       // ---- 16 band chunks: chunk r = halo row r; this lane's entries are Gx[(r - bpy, k - res)] at columns 4 wq + k
 #pragma unroll 1
-      for (int r = 0; r < HY; ++r, ++cnt) {
+      for (int r = 0; r < HY; ++r) {
         const int ey = r - bpy;
         const bool rowv = ey >= 0 && ey < D;
         // a halo row outside this lane's 9 displacement rows reads the zero planes instead (one select on the address)
