@@ -17,7 +17,9 @@
 //     by the load address (shared-memory column of the lane, plane k - (x & 3)), six of the twelve values need a select.
 //   * S is the B operand: one TMA box (32 x 1 x N, SWIZZLE_128B) per halo row lands as a K-major operand tile, zero
 //     outside the image for free.  fp32 parity (1e-5 of max|ref|) needs 3xTF32: Gx is split while the band row is built,
-//     S by four "split" warps (hi = tf32(v) in place, lo = v - hi next to it); three products hi*hi + lo*hi + hi*lo.
+//     S by one "split" warp per gradient (hi = tf32(v) in place, lo = v - hi next to it); three products hi*hi + hi*lo + lo*hi
+//     into partial accumulators summed in the drain -- with three of them the two products that share the band's hi part are
+//     ONE MMA of N = 2 N_pad over the adjacent hi / lo operand tiles (an MMA costs ~70 cycles here whatever N is).
 //   * Two 4-warp groups work side by side, one per gradient, each with its own accumulator, band ring and operand stages:
 //     stage Gx of its tile (coalesced loads, LeakyReLU mask applied on the way, private shared-memory columns) -> build 16
 //     band chunks -> stage the next tile's Gx -> drain the accumulators (tcgen05.ld) and store.  With a flow the second
